@@ -1,0 +1,240 @@
+/*
+ * spgnn_b200 — C ABI of the B200-native SPGNN GNN-stage kernels (libspgnn_b200.so).
+ *
+ * The reference (DIAGNijmegen/spgnn) is pure Python and reaches its arithmetic through
+ * DGL's Python API (models.py:8).  There is no FFI in the reference to mirror, so each
+ * entry point below names the reference call site / DGL operator it replaces.  The
+ * reference-side binding a maintainer would add is the ctypes stub in INTEGRATION.md
+ * (spgnn_b200/_lib.py is that stub, as shipped).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller
+ *     (PyTorch) owns all memory; nothing is allocated, retained or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered on it,
+ *     no call synchronises the device; calls are re-entrant and keep no global state;
+ *   - return 0 on success, <0 on error (SPGNN_E_*); text via spgnn_last_error()
+ *     (thread-local);
+ *   - float tensors are fp32 row-major with an explicit leading dimension (ld*, in
+ *     elements); "idx" tensors are int32 unless stated int64 (the DGL-visible ones).
+ *   - N = nodes in the batch, E = directed edges incl. self loops, B = graphs,
+ *     H = heads, F = out feats per head.
+ */
+#ifndef SPGNN_B200_H
+#define SPGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPGNN_OK            0
+#define SPGNN_E_INVALID    -1   /* bad argument (shape, alignment, null) */
+#define SPGNN_E_CUDA       -2   /* a CUDA runtime call failed */
+#define SPGNN_E_UNSUPPORTED -3  /* shape outside what the kernels were built for */
+#define SPGNN_E_WORKSPACE  -4   /* workspace too small */
+
+#define SPGNN_ACT_NONE 0
+#define SPGNN_ACT_ELU  1
+#define SPGNN_ACT_TANH 2
+#define SPGNN_ACT_RELU 3
+#define SPGNN_ACT_LEAKY 4      /* slope passed separately */
+
+const char* spgnn_last_error(void);
+int  spgnn_abi_version(void);
+/* SM count etc. of the current device (used by the host side to size workspaces). */
+int  spgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * Graph construction and batching.
+ * Replaces: nx.DiGraph(adj) -> DGLGraph -> dgl.remove_self_loop -> g.add_edges(nodes,nodes)
+ *           (job_runner.py:1779-1801, :1319-1344, :822-838) and dgl.batch (job_runner.py:1390,
+ *           :1882, :2046).  Integer work: results are bit-identical to DGL's.
+ * ---------------------------------------------------------------------------------- */
+
+/* Exclusive prefix scan of int64 counts: out[0]=0, out[i+1]=out[i]+in[i], n inputs, n+1 outputs.
+ * ws: at least spgnn_scan_ws_bytes(n) bytes. */
+int64_t spgnn_scan_ws_bytes(int64_t n);
+int spgnn_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* ws, void* stream);
+
+/* Dense adjacency -> DGL edge list, per graph.
+ *   adj      uint8, graphs concatenated; graph g is an n_g x n_g row-major block at adj_off[g]
+ *   n_nodes  int64 [B]; adj_off int64 [B+1] (= scan of n_g^2); node_off int64 [B+1]
+ * pass 1 (count): row_cnt[int64, N] = off-diagonal non-zeros per row; n_edges[int64,B] = sum + n_g
+ * pass 2 (fill):  given edge_off = scan(n_edges) and row_off = scan over rows of row_cnt (int64 [N+1]),
+ *                 writes LOCAL src/dst int64 [E]: off-diagonal non-zeros in row-major order, then (k,k), k<n_g. */
+int spgnn_adj_count(const uint8_t* adj, const int64_t* adj_off, const int64_t* n_nodes, const int64_t* node_off,
+                    int64_t B, int64_t N, int64_t* row_cnt, int64_t* n_edges, void* stream);
+int spgnn_adj_fill(const uint8_t* adj, const int64_t* adj_off, const int64_t* n_nodes, const int64_t* node_off,
+                   const int64_t* edge_off, const int64_t* row_off, int64_t B, int64_t N,
+                   int64_t* src_local, int64_t* dst_local, void* stream);
+
+/* dgl.batch + CSC/CSR build.
+ *   in : node_off/edge_off int64 [B+1]; src_local/dst_local int64 [E] (per-graph local ids, DGL edge order)
+ *   out: src/dst int64 [E] global ids (== dgl.batch(...).edges());
+ *        node_gid int32 [N];
+ *        in_ptr int32 [N+1], in_src int32 [E], in_eid int32 [E]   — in-edges of each node, ascending edge id
+ *        out_ptr int32 [N+1], out_dst int32 [E], out_slot int32 [E] — out-edges; out_slot = position in in_* arrays
+ *        flags int32 [2]: [0] = number of zero-in-degree nodes, [1] = number of out-of-range endpoints
+ *   ws : spgnn_batch_ws_bytes(N, E) bytes of scratch. */
+int64_t spgnn_batch_ws_bytes(int64_t N, int64_t E);
+int spgnn_batch_build(const int64_t* node_off, const int64_t* edge_off, int64_t B, int64_t N, int64_t E,
+                      const int64_t* src_local, const int64_t* dst_local,
+                      int64_t* src, int64_t* dst, int32_t* node_gid,
+                      int32_t* in_ptr, int32_t* in_src, int32_t* in_eid,
+                      int32_t* out_ptr, int32_t* out_dst, int32_t* out_slot,
+                      int32_t* flags, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense projection (DGL GATConv.fc / res_fc, GraphConv weight, SAGEConv fc_*, GIN MLP, gnn_out):
+ * SURVEY §2.1 K1/K8.  fp32 in, fp32 out.
+ *   C[M,N] (ldc) = [A1 | A2][M,K1+K2] * W[N, K1+K2 (ldw)]^T  (+ bias[N]) (act)
+ * A2 may be null (K2 = 0): the two-source form removes torch.cat([h_s,h_p]) (models.py:477,481).
+ * mode: 0 = fp32 SIMT, 1 = tcgen05 bf16x3 split (error-compensated, ~2^-17 rel), -1 = library default.
+ * ---------------------------------------------------------------------------------- */
+int spgnn_linear_fwd(const float* A1, int64_t lda1, int64_t K1, const float* A2, int64_t lda2, int64_t K2,
+                     const float* W, int64_t ldw, const float* bias, int act, float slope,
+                     float* C, int64_t ldc, int64_t M, int64_t N, int mode, void* stream);
+/* dA[M,K] (ldda) = dC[M,N] (lddc) * W[N, k_off : k_off+K] (ldw) */
+int spgnn_linear_bwd_input(const float* dC, int64_t lddc, const float* W, int64_t ldw, int64_t k_off,
+                           float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K, int mode, void* stream);
+/* dW[N, k_off : k_off+K] (lddw) = dC[M,N]^T * A[M,K] (lda); split over M into `splits` partial sums in ws
+ * (splits*N*K floats, see spgnn_linear_bwd_weight_ws) that a second kernel reduces deterministically. */
+int64_t spgnn_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K);
+int spgnn_linear_bwd_weight(const float* dC, int64_t lddc, const float* A, int64_t lda,
+                            float* dW, int64_t lddw, int64_t k_off, int64_t M, int64_t N, int64_t K,
+                            void* ws, int mode, void* stream);
+/* out[n] = sum_m X[m, n]  (bias gradients).  ws: spgnn_colsum_ws(N) bytes. */
+int64_t spgnn_colsum_ws(int64_t N);
+int spgnn_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * GAT edge-softmax + aggregation + residual + bias + activation (+ head mean), fused.
+ * Replaces DGL GATConv.forward K3-K9 as called at models.py:324,326,478,479,482,535,538.
+ *   Y   [N, ldy]: cols [0,HF) z;  [res_off, res_off+HF) residual projection (res_mode 1);
+ *                 el at col el_off+h, er at col er_off+h  (logits come out of the projection as
+ *                 extra columns: el = x . (W_fc^T attn_l))
+ *   res_mode 0 none, 1 linear (in Y), 2 identity: xres [N, ldxres] viewed [N, -1, F] (D == F -> broadcast)
+ *   out [N, ldo]: HF wide, or F wide when mean_heads
+ *   att [E, H] : softmax weights per in-edge slot (before dropout), saved for backward
+ *   attn dropout: keep-prob 1-p, mask = hash(seed, slot*H+h); p = 0 disables.
+ * ---------------------------------------------------------------------------------- */
+int spgnn_gat_agg_fwd(const float* Y, int64_t ldy, int64_t res_off, int64_t el_off, int64_t er_off,
+                      int res_mode, const float* xres, int64_t ldxres, int64_t xres_cols,
+                      const float* bias, int act, float negative_slope, int mean_heads,
+                      float attn_drop_p, uint64_t seed,
+                      const int32_t* in_ptr, const int32_t* in_src,
+                      int64_t N, int64_t H, int64_t F,
+                      float* out, int64_t ldo, float* att, void* stream);
+/* Backward.  g_out [N, ldg] (HF or F wide when mean_heads); out = saved forward output (ignored when
+ * mean_heads: pre-activations are recomputed); writes dY [N, ldy] (same column layout as Y: dz, dres, del,
+ * der) and, for res_mode 2, dxres [N, ldxres] (overwritten).  The bias gradient is the column sum of g:
+ * for res_mode 1 that is spgnn_colsum over the dres columns of dY, otherwise over g_ws.
+ * g_ws: float [N, H*F] (only read/written when res_mode != 1); ds_ws: float [E*H] scratch. */
+int spgnn_gat_agg_bwd(const float* g_out, int64_t ldg, const float* out, int64_t ldo,
+                      const float* Y, int64_t ldy, int64_t res_off, int64_t el_off, int64_t er_off,
+                      int res_mode, const float* xres, int64_t ldxres, int64_t xres_cols,
+                      const float* bias, int act, float negative_slope, int mean_heads,
+                      float attn_drop_p, uint64_t seed, const float* att,
+                      const int32_t* in_ptr, const int32_t* in_src,
+                      const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot,
+                      int64_t N, int64_t H, int64_t F,
+                      float* dY, float* dxres, float* g_ws, float* ds_ws, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Weighted-sum aggregation (DGL SpMM copy_u.sum with degree norms): GraphConv and GINConv-mean.
+ *   out[v, :] = act( post[v] * sum_{s in seg(v)} pre[nbr[s]] * x[nbr[s], :] + self_coef * x[v, :] + bias )
+ * pre/post/bias may be null; self_coef is read from device memory (GIN's 1+eps) when self_coef_ptr != null
+ * (value = 1 + *self_coef_ptr), else 0.  Forward uses the in-CSC, backward the out-CSR with pre/post swapped.
+ * Replaces GraphConv (models.py:172-182) and GINConv "mean" (models.py:358-383) message passing.
+ * ---------------------------------------------------------------------------------- */
+int spgnn_spmm(const float* x, int64_t ldx, const int32_t* ptr, const int32_t* nbr,
+               const float* pre, const float* post, const float* self_eps_ptr,
+               const float* bias, int act, float slope,
+               float* out, int64_t ldo, int64_t N, int64_t F, void* stream);
+/* deg^-1/2 and 1/deg (clamped at 1) from a ptr array: norm_sqrt[N], norm_inv[N] (either may be null) */
+int spgnn_degree_norms(const int32_t* ptr, int64_t N, float* norm_sqrt, float* norm_inv, void* stream);
+
+/* SAGEConv "pool": neigh[v,f] = max_{u->v} m[u,f]; arg[v,f] = in-slot of the max (first max).
+ * Backward: dm[u,f] = sum over out-edges (u->v, slot s) of g[v,f] * [arg[v,f] == s].
+ * Replaces DGL SpMM copy_u.max (models.py:668-679). */
+int spgnn_sage_maxpool_fwd(const float* m, int64_t ldm, const int32_t* in_ptr, const int32_t* in_src,
+                           float* out, int64_t ldo, int32_t* arg, int64_t N, int64_t F, void* stream);
+int spgnn_sage_maxpool_bwd(const float* g, int64_t ldg, const int32_t* arg,
+                           const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot,
+                           float* dm, int64_t lddm, int64_t N, int64_t F, void* stream);
+
+/* Elementwise helpers the layer stacks need between projections.
+ *   bias_act      : y = act(x + bias)           (GraphConv aggregate-first epilogue, GIN MLP, SAGE output)
+ *   act_bwd       : dx = g * act'(y)  from the saved OUTPUT y (elu/tanh/relu/leaky all invertible this way)
+ *   concat_dropout: out[:, :K1] = drop(x1), out[:, K1:K1+K2] = drop(x2), scaled by 1/(1-p); mask = hash(seed, idx)
+ *                   (GATConv feat_drop on torch.cat([h_s,h_p]), models.py:431-435,477); bwd applies the same mask. */
+int spgnn_bias_act(const float* x, int64_t ldx, const float* bias, int act, float slope,
+                   float* y, int64_t ldy, int64_t M, int64_t N, void* stream);
+int spgnn_act_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, int act, float slope,
+                  float* dx, int64_t lddx, int64_t M, int64_t N, void* stream);
+int spgnn_concat_dropout(const float* x1, int64_t ld1, int64_t K1, const float* x2, int64_t ld2, int64_t K2,
+                         float p, uint64_t seed, float* out, int64_t ldo, int64_t M, void* stream);
+int spgnn_concat_dropout_bwd(const float* g, int64_t ldg, int64_t K1, int64_t K2, float p, uint64_t seed,
+                             float* d1, int64_t ldd1, float* d2, int64_t ldd2, int64_t M, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Positional-encoding inits on device.
+ *   anchor_select : job_runner.py:1727-1757 + :1712-1725 — softmax(fvs_out), 21 x masked column arg-max (first
+ *                   max), then for the first 18 anchors the farthest descendant leaf in the DAG
+ *                   {u->v : u<v adjacent} (ties -> largest index; the anchor itself when it has no descendant).
+ *                   anchors int32 [B, pos_dim] LOCAL node ids; pos_dim in {21, 39}.
+ *   pe_dist_init  : job_runner.py:1759-1777 — pos_enc[n,k] = hops(n, anchor_k)/diameter on the self-loop-free
+ *                   graph (all-pairs bit-parallel BFS per graph gives the diameter); diam int32 [B];
+ *                   flags[0] counts disconnected graphs.
+ *   pe_rw_init    : job_runner.py:1684-1702 — diag((A D^-1)^k), k=1..pos_dim, fp64 accumulate, fp32 out.
+ * All take a batched adjacency (ptr, nbr; self loops are skipped) and node_off int64 [B+1].  pe_dist_init follows
+ * nx shortest paths v -> anchor, so pass the OUT-CSR (out_ptr, out_dst); the others take the in-CSC.  For the
+ * symmetric adjacencies the reference builds (dataset.py:418-419) the two are the same graph.
+ * ---------------------------------------------------------------------------------- */
+int spgnn_anchor_select(const float* fvs_out, int64_t ld, int64_t n_class,
+                        const int64_t* node_off, const int32_t* in_ptr, const int32_t* in_src,
+                        int64_t B, int64_t pos_dim, int64_t max_nodes, int32_t* anchors, void* stream);
+int64_t spgnn_pe_dist_ws_bytes(int64_t B, int64_t max_nodes);
+int spgnn_pe_dist_init(const int64_t* node_off, const int32_t* in_ptr, const int32_t* in_src,
+                       const int32_t* anchors, int64_t B, int64_t pos_dim, int64_t max_nodes,
+                       float* pos_enc, int64_t ldp, int32_t* diam, int32_t* flags, void* ws, void* stream);
+int spgnn_pe_rw_init(const int64_t* node_off, const int32_t* in_ptr, const int32_t* in_src,
+                     int64_t B, int64_t pos_dim, int64_t max_nodes, float* pos_enc, int64_t ldp, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Decision rule and loss (callers of the path).
+ *   segmented_argmax : job_runner.py:158-165 — per graph, per class c in [1, n_class): the node with the highest
+ *                      softmax probability of class c (first max); out int64 [B, n_class-1] GLOBAL node ids.
+ *   masked_ce_fwd/bwd: job_runner.py:1885-1900 — F.cross_entropy(out[mask], y[mask], weight): sums[0] = sum w*nll,
+ *                      sums[1] = sum w over kept nodes (double[2], zeroed by the call); keep = (y != 0) || u01(hash(seed,node)) < rate, or an explicit
+ *                      uint8 mask when mask != null.  bwd: dlogits = keep * w_y * (softmax - onehot) * (scale / sums[1]).
+ * ---------------------------------------------------------------------------------- */
+int spgnn_segmented_argmax(const float* logits, int64_t ld, int64_t n_class, const int64_t* node_off, int64_t B,
+                           int64_t* out, void* stream);
+int spgnn_masked_ce_fwd(const float* logits, int64_t ld, int64_t n_class, const int64_t* y, const uint8_t* mask,
+                        float rate, uint64_t seed, const float* class_w, int64_t N, double* sums, void* stream);
+int spgnn_masked_ce_bwd(const float* logits, int64_t ld, int64_t n_class, const int64_t* y, const uint8_t* mask,
+                        float rate, uint64_t seed, const float* class_w, const double* sums, float scale,
+                        int64_t N, float* dlogits, int64_t ldd, void* stream);
+/* SGD with momentum over a flat bucket (torch.optim.SGD semantics: buf = mu*buf + g; p -= lr*buf). */
+int spgnn_sgd_momentum(float* p, const float* g, float* buf, int64_t n, float lr, float mu, float grad_scale,
+                       int first_step, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Synthetic airway trees on device (bench input; integer part bit-identical to spgnn_b200/synth.py).
+ * ---------------------------------------------------------------------------------- */
+int spgnn_synth_trees(int64_t first_tree, int64_t B, uint32_t seed, int ragged, int64_t k_fixed,
+                      const int64_t* node_off, int64_t* parent_local, int64_t* labels, void* stream);
+int spgnn_synth_sizes(int64_t first_tree, int64_t B, uint32_t seed, int ragged, int64_t k_fixed,
+                      int64_t* n_nodes, int64_t* n_edges, void* stream);
+int spgnn_synth_edges(const int64_t* node_off, const int64_t* edge_off, const int64_t* parent_local, int64_t B,
+                      int64_t* src_local, int64_t* dst_local, void* stream);
+int spgnn_synth_features(int64_t first_tree, int64_t B, uint32_t seed, const int64_t* node_off, int64_t N,
+                         float* fvs, int64_t ldf, int64_t fv_dim, float* fvs_out, int64_t ldo, int64_t n_class,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPGNN_B200_H */

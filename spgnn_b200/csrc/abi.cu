@@ -1,0 +1,38 @@
+// Error reporting, version and device queries of the C ABI.
+#include "common.cuh"
+#include <string.h>
+
+namespace spgnn {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+        cached = p.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+}  // namespace spgnn
+
+extern "C" const char* spgnn_last_error(void) { return spgnn::g_err; }
+extern "C" int spgnn_abi_version(void) { return 1; }
+extern "C" int spgnn_device_info(int* sm, int* major, int* minor) {
+    int dev = 0;
+    SPGNN_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    SPGNN_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    if (sm) *sm = p.multiProcessorCount;
+    if (major) *major = p.major;
+    if (minor) *minor = p.minor;
+    return SPGNN_OK;
+}

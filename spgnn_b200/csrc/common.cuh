@@ -1,0 +1,92 @@
+// Shared device/host helpers for libspgnn_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/spgnn_b200.h"
+
+namespace spgnn {
+
+void set_error(const char* fmt, ...);
+
+#define SPGNN_REQUIRE(cond, ...)                               \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            spgnn::set_error(__VA_ARGS__);                     \
+            return SPGNN_E_INVALID;                            \
+        }                                                      \
+    } while (0)
+
+#define SPGNN_CUDA_OK(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            spgnn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SPGNN_E_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define SPGNN_LAUNCH_OK() SPGNN_CUDA_OK(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+int sm_count();
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// activation on the pre-activation x
+__device__ __forceinline__ float act_fwd(float x, int act, float slope) {
+    switch (act) {
+        case SPGNN_ACT_ELU: return x > 0.f ? x : expm1f(x);
+        case SPGNN_ACT_TANH: return tanhf(x);
+        case SPGNN_ACT_RELU: return fmaxf(x, 0.f);
+        case SPGNN_ACT_LEAKY: return x > 0.f ? x : slope * x;
+        default: return x;
+    }
+}
+// derivative expressed through the OUTPUT y = act(x)
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
+    switch (act) {
+        case SPGNN_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+        case SPGNN_ACT_TANH: return 1.f - y * y;
+        case SPGNN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case SPGNN_ACT_LEAKY: return y > 0.f ? 1.f : slope;
+        default: return 1.f;
+    }
+}
+
+// Counter-based hash -> uniform in [0,1): two rounds of a 64-bit finaliser (splitmix64).  Used for
+// dropout / node-sampling masks so that backward can regenerate the forward mask from (seed, index).
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
+    uint64_t h = mix64(seed ^ mix64(idx));
+    return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);   // 24 random bits
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace spgnn

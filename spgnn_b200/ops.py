@@ -1,0 +1,352 @@
+"""autograd.Function wrappers over the C ABI (include/spgnn_b200.h).  PyTorch here is plumbing: it owns the
+device memory and the autograd tape; every arithmetic step below is one of this repo's CUDA kernels.
+
+No fallbacks: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from ._lib import SpgnnError, lib, ptr, require_cuda, stream
+
+ACT = {None: 0, "none": 0, "elu": 1, "tanh": 2, "relu": 3, "leaky_relu": 4}
+
+# projection arithmetic: 0 = fp32 SIMT, 1 = tcgen05 split-bf16 tensor cores (see csrc/gemm_tc.cu)
+GEMM_MODE = 0
+
+_seed_state = {"seed": 0x5350474E, "counter": 0}
+
+
+def manual_seed(seed: int):
+    """Seed of the dropout / node-sampling masks (counter-hash based, regenerated in backward)."""
+    _seed_state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _seed_state["counter"] = 0
+
+
+def next_seed() -> int:
+    _seed_state["counter"] += 1
+    return (_seed_state["seed"] * 0x9E3779B97F4A7C15 + _seed_state["counter"] * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+def act_code(act):
+    """Map an activation given as a name, None or a torch callable (F.elu, torch.tanh, ...) to the ABI code."""
+    if act is None or isinstance(act, str):
+        return ACT[act]
+    name = getattr(act, "__name__", "")
+    if name in ("elu", "tanh", "relu", "leaky_relu"):
+        return ACT[name]
+    raise SpgnnError(f"unsupported activation {act!r} (supported: elu, tanh, relu, leaky_relu, None)")
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _rows(t):
+    """Row-major 2-D view requirements: unit inner stride."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def empty_padded(rows, cols, device):
+    """[rows, cols] fp32 view of a buffer whose leading dimension is padded to a multiple of 4 (16-byte rows)."""
+    return torch.empty(rows, _pad4(cols), dtype=torch.float32, device=device)[:, :cols]
+
+
+def colsum(x):
+    x = _rows(x)
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(lib().colsum_ws(N)), dtype=torch.uint8, device=x.device)
+    lib().colsum(ptr(x), x.stride(0), M, N, ptr(out), ptr(ws), stream())
+    return out
+
+
+class LinearFn(Function):
+    """y = act([x1 | x2] @ W^T + bias).  W is [N, K1+K2] with unit inner stride (any row stride)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, W, bias, act, slope):
+        require_cuda(x1, x2, W, bias)
+        x1 = _rows(x1)
+        x2 = _rows(x2) if x2 is not None else None
+        W = _rows(W)
+        M, K1 = x1.shape
+        K2 = x2.shape[1] if x2 is not None else 0
+        N = W.shape[0]
+        if W.shape[1] != K1 + K2:
+            raise SpgnnError(f"linear: weight has {W.shape[1]} columns, input has {K1}+{K2}")
+        y = empty_padded(M, N, x1.device)
+        b = bias.contiguous() if bias is not None else None
+        lib().linear_fwd(ptr(x1), x1.stride(0), K1, ptr(x2), x2.stride(0) if x2 is not None else 0, K2,
+                         ptr(W), W.stride(0), ptr(b), act, float(slope), ptr(y), y.stride(0), M, N, GEMM_MODE, stream())
+        ctx.save_for_backward(x1, x2, W, y if act else None)
+        ctx.cfg = (act, float(slope), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, W, y = ctx.saved_tensors
+        act, slope, has_bias = ctx.cfg
+        L = lib()
+        g = _rows(g)
+        M, N = g.shape
+        K1 = x1.shape[1]
+        K2 = x2.shape[1] if x2 is not None else 0
+        if act:
+            d = empty_padded(M, N, g.device)
+            L.act_bwd(ptr(g), g.stride(0), ptr(y), y.stride(0), act, slope, ptr(d), d.stride(0), M, N, stream())
+            g = d
+        dx1 = dx2 = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx1 = empty_padded(M, K1, g.device)
+            L.linear_bwd_input(ptr(g), g.stride(0), ptr(W), W.stride(0), 0, ptr(dx1), dx1.stride(0), M, N, K1,
+                               GEMM_MODE, stream())
+        if x2 is not None and ctx.needs_input_grad[1]:
+            dx2 = empty_padded(M, K2, g.device)
+            L.linear_bwd_input(ptr(g), g.stride(0), ptr(W), W.stride(0), K1, ptr(dx2), dx2.stride(0), M, N, K2,
+                               GEMM_MODE, stream())
+        if ctx.needs_input_grad[2]:
+            dW = empty_padded(N, K1 + K2, g.device)
+            for x, koff, K in ((x1, 0, K1), (x2, K1, K2)):
+                if x is None:
+                    continue
+                ws = torch.empty(max(int(L.linear_bwd_weight_ws(M, N, K)), 16), dtype=torch.uint8, device=g.device)
+                L.linear_bwd_weight(ptr(g), g.stride(0), ptr(x), x.stride(0), ptr(dW), dW.stride(0), koff, M, N, K,
+                                    ptr(ws), GEMM_MODE, stream())
+        if has_bias and ctx.needs_input_grad[3]:
+            db = colsum(g)
+        return dx1, dx2, dW, db, None, None
+
+
+def linear(x1, W, bias=None, act=None, slope=0.0, x2=None):
+    return LinearFn.apply(x1, x2, W, bias, act_code(act), slope)
+
+
+class ConcatDropoutFn(Function):
+    """out = dropout(cat([x1, x2], 1), p) with a hash mask regenerated in backward (GATConv feat_drop)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, p, seed):
+        require_cuda(x1, x2)
+        x1 = _rows(x1)
+        x2 = _rows(x2) if x2 is not None else None
+        M, K1 = x1.shape
+        K2 = x2.shape[1] if x2 is not None else 0
+        out = empty_padded(M, K1 + K2, x1.device)
+        lib().concat_dropout(ptr(x1), x1.stride(0), K1, ptr(x2), x2.stride(0) if x2 is not None else 0, K2, float(p),
+                             seed, ptr(out), out.stride(0), M, stream())
+        ctx.cfg = (K1, K2, float(p), seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        K1, K2, p, seed = ctx.cfg
+        g = _rows(g)
+        M = g.shape[0]
+        d1 = empty_padded(M, K1, g.device) if ctx.needs_input_grad[0] else None
+        d2 = empty_padded(M, K2, g.device) if (K2 and ctx.needs_input_grad[1]) else None
+        lib().concat_dropout_bwd(ptr(g), g.stride(0), K1, K2, p, seed, ptr(d1), d1.stride(0) if d1 is not None else 0,
+                                 ptr(d2), d2.stride(0) if d2 is not None else 0, M, stream())
+        return d1, d2, None, None
+
+
+def concat_dropout(x1, x2, p, training):
+    p = float(p) if training else 0.0
+    if p == 0.0 and x2 is None:
+        return x1
+    return ConcatDropoutFn.apply(x1, x2, p, next_seed())
+
+
+class BiasActFn(Function):
+    @staticmethod
+    def forward(ctx, x, bias, act, slope):
+        require_cuda(x, bias)
+        x = _rows(x)
+        M, N = x.shape
+        y = empty_padded(M, N, x.device)
+        lib().bias_act(ptr(x), x.stride(0), ptr(bias), act, float(slope), ptr(y), y.stride(0), M, N, stream())
+        ctx.save_for_backward(y)
+        ctx.cfg = (act, float(slope), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        act, slope, has_bias = ctx.cfg
+        g = _rows(g)
+        M, N = g.shape
+        d = empty_padded(M, N, g.device)
+        lib().act_bwd(ptr(g), g.stride(0), ptr(y), y.stride(0), act, slope, ptr(d), d.stride(0), M, N, stream())
+        return d, (colsum(d) if has_bias and ctx.needs_input_grad[1] else None), None, None
+
+
+def bias_act(x, bias=None, act=None, slope=0.0):
+    return BiasActFn.apply(x, bias, act_code(act), slope)
+
+
+class GatAggFn(Function):
+    """Fused edge-softmax + aggregation + residual + bias + activation (+ head mean) over the projection output Y."""
+
+    @staticmethod
+    def forward(ctx, Y, xres, bias, graph, H, F, res_mode, act, neg_slope, mean_heads, drop_p, seed):
+        require_cuda(Y, xres, bias)
+        Y = _rows(Y)
+        N = Y.shape[0]
+        HF = H * F
+        res_off = HF
+        el_off = 2 * HF if res_mode == 1 else HF
+        er_off = el_off + H
+        if Y.shape[1] != er_off + H:
+            raise SpgnnError(f"gat_agg: projection has {Y.shape[1]} columns, expected {er_off + H}")
+        xr = _rows(xres) if res_mode == 2 else None
+        out = empty_padded(N, F if mean_heads else HF, Y.device)
+        att = torch.empty(graph.num_edges, H, dtype=torch.float32, device=Y.device)
+        b = bias.contiguous() if bias is not None else None
+        lib().gat_agg_fwd(ptr(Y), Y.stride(0), res_off, el_off, er_off, res_mode, ptr(xr),
+                          xr.stride(0) if xr is not None else 0, xr.shape[1] if xr is not None else 0, ptr(b), act,
+                          float(neg_slope), int(mean_heads), float(drop_p), seed, ptr(graph.in_ptr), ptr(graph.in_src),
+                          N, H, F, ptr(out), out.stride(0), ptr(att), stream())
+        ctx.save_for_backward(Y, xr, b, out if not mean_heads else None, att)
+        ctx.graph = graph
+        ctx.cfg = (H, F, res_mode, act, float(neg_slope), int(mean_heads), float(drop_p), seed, res_off, el_off, er_off)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        Y, xr, b, out, att = ctx.saved_tensors
+        H, F, res_mode, act, neg_slope, mean_heads, drop_p, seed, res_off, el_off, er_off = ctx.cfg
+        gr = ctx.graph
+        g = _rows(g)
+        N, HF = Y.shape[0], H * F
+        dY = torch.empty(N, Y.stride(0), dtype=torch.float32, device=Y.device)[:, :Y.shape[1]]
+        g_ws = torch.empty(N, HF, dtype=torch.float32, device=Y.device) if res_mode != 1 else None
+        dxres = torch.empty(N, xr.stride(0), dtype=torch.float32, device=Y.device)[:, :xr.shape[1]] \
+            if res_mode == 2 else None
+        ds = torch.empty(gr.num_edges * H, dtype=torch.float32, device=Y.device)
+        lib().gat_agg_bwd(ptr(g), g.stride(0), ptr(out), out.stride(0) if out is not None else 0, ptr(Y), Y.stride(0),
+                          res_off, el_off, er_off, res_mode, ptr(xr), xr.stride(0) if xr is not None else 0,
+                          xr.shape[1] if xr is not None else 0, ptr(b), act, neg_slope, mean_heads, drop_p, seed,
+                          ptr(att), ptr(gr.in_ptr), ptr(gr.in_src), ptr(gr.out_ptr), ptr(gr.out_dst), ptr(gr.out_slot),
+                          N, H, F, ptr(dY), ptr(dxres), ptr(g_ws), ptr(ds), stream())
+        db = None
+        if b is not None and ctx.needs_input_grad[2]:
+            db = colsum(dY[:, res_off:res_off + HF] if res_mode == 1 else g_ws)
+        return dY, dxres, db, None, None, None, None, None, None, None, None, None
+
+
+class SpmmFn(Function):
+    """out = act(post ⊙ Σ_{u→v} pre[u]·x[u] + (1+eps)·x[v]·[eps given] + bias)  — GraphConv / GINConv-mean."""
+
+    @staticmethod
+    def forward(ctx, x, eps, bias, graph, pre, post, act, slope):
+        require_cuda(x, eps, bias)
+        x = _rows(x)
+        N, F = x.shape
+        out = empty_padded(N, F, x.device)
+        b = bias.contiguous() if bias is not None else None
+        lib().spmm(ptr(x), x.stride(0), ptr(graph.in_ptr), ptr(graph.in_src), ptr(pre), ptr(post), ptr(eps), ptr(b),
+                   act, float(slope), ptr(out), out.stride(0), N, F, stream())
+        ctx.save_for_backward(x if eps is not None else None, eps, out if act else None)
+        ctx.graph, ctx.pre, ctx.post = graph, pre, post
+        ctx.cfg = (act, float(slope), b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, eps, out = ctx.saved_tensors
+        act, slope, has_bias = ctx.cfg
+        gr = ctx.graph
+        L = lib()
+        g = _rows(g)
+        N, F = g.shape
+        if act:
+            d = empty_padded(N, F, g.device)
+            L.act_bwd(ptr(g), g.stride(0), ptr(out), out.stride(0), act, slope, ptr(d), d.stride(0), N, F, stream())
+            g = d
+        dx = deps = db = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_padded(N, F, g.device)
+            # transpose graph: out-edges, with the roles of the two norms swapped
+            L.spmm(ptr(g), g.stride(0), ptr(gr.out_ptr), ptr(gr.out_dst), ptr(ctx.post), ptr(ctx.pre), ptr(eps), None,
+                   0, 0.0, ptr(dx), dx.stride(0), N, F, stream())
+        if eps is not None and ctx.needs_input_grad[1]:
+            deps = (g * x).sum().reshape(1)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = colsum(g)
+        return dx, deps, db, None, None, None, None, None
+
+
+class MaxPoolFn(Function):
+    """neigh[v] = max over in-neighbours (SAGEConv 'pool'), arg-slot saved for the backward scatter."""
+
+    @staticmethod
+    def forward(ctx, m, graph):
+        require_cuda(m)
+        m = _rows(m)
+        N, F = m.shape
+        out = empty_padded(N, F, m.device)
+        arg = torch.empty(N, F, dtype=torch.int32, device=m.device)
+        lib().sage_maxpool_fwd(ptr(m), m.stride(0), ptr(graph.in_ptr), ptr(graph.in_src), ptr(out), out.stride(0),
+                               ptr(arg), N, F, stream())
+        ctx.save_for_backward(arg)
+        ctx.graph = graph
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        gr = ctx.graph
+        g = _rows(g)
+        N, F = g.shape
+        dm = empty_padded(N, F, g.device)
+        lib().sage_maxpool_bwd(ptr(g), g.stride(0), ptr(arg), ptr(gr.out_ptr), ptr(gr.out_dst), ptr(gr.out_slot),
+                               ptr(dm), dm.stride(0), N, F, stream())
+        return dm, None
+
+
+class MaskedCEFn(Function):
+    """F.cross_entropy(logits[mask], y[mask], weight) with the node mask either given or drawn on device
+    (keep = y != 0 or u < rate), job_runner.py:1885-1900.  ``extra`` (sum of class weights from other ranks) lets
+    data-parallel training normalise by the global Σw."""
+
+    @staticmethod
+    def forward(ctx, logits, y, mask, rate, seed, class_w, reduce_fn):
+        require_cuda(logits, y, mask, class_w)
+        logits = _rows(logits)
+        N, C = logits.shape
+        sums = torch.empty(2, dtype=torch.float64, device=logits.device)
+        m = mask.to(torch.uint8).contiguous() if mask is not None else None
+        lib().masked_ce_fwd(ptr(logits), logits.stride(0), C, ptr(y), ptr(m), float(rate), seed, ptr(class_w), N,
+                            ptr(sums), stream())
+        if reduce_fn is not None:
+            sums = reduce_fn(sums)          # all-reduce (Σ w·nll, Σ w) across ranks
+        ctx.save_for_backward(logits, y, m, class_w, sums)
+        ctx.cfg = (float(rate), seed)
+        return (sums[0] / sums[1]).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, y, m, class_w, sums = ctx.saved_tensors
+        rate, seed = ctx.cfg
+        N, C = logits.shape
+        d = empty_padded(N, C, logits.device)
+        lib().masked_ce_bwd(ptr(logits), logits.stride(0), C, ptr(y), ptr(m), rate, seed, ptr(class_w), ptr(sums),
+                            1.0, N, ptr(d), d.stride(0), stream())
+        return d * g, None, None, None, None, None, None
+
+
+def masked_cross_entropy(logits, y, class_w, mask=None, rate=1.0, seed=None, reduce_fn=None):
+    return MaskedCEFn.apply(logits, y, mask, rate, next_seed() if seed is None else seed, class_w, reduce_fn)
+
+
+def segmented_argmax(logits, graph):
+    """job_runner.py:158-165: per tree and class 1..C-1 the node (global id) with the highest softmax probability."""
+    require_cuda(logits)
+    logits = _rows(logits)
+    C = logits.shape[1]
+    out = torch.empty(graph.batch_size, C - 1, dtype=torch.int64, device=logits.device)
+    lib().segmented_argmax(ptr(logits), logits.stride(0), C, ptr(graph.node_off), graph.batch_size, ptr(out), stream())
+    return out

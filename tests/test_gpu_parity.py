@@ -1,0 +1,344 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference-generated fixtures.
+
+Bars (BASELINE.json north_star): batching / index arithmetic bit-exact; fp32 logits and positional encodings
+within 1e-4 relative; arg-max decisions identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (FULL_MODELS, TINY_MODELS, golden_graph_inputs, golden_state_dict, load_golden, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # north_star tolerance for fp32 logits / encodings
+GRAD_TOL = 2e-4     # gradients: same bar, a little head-room for the split-order of the weight-gradient reduction
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from oracle import dgl_ops, models as om, pe as ope
+    from spgnn_b200 import graph as sg, models as sm, ops, pe as spe, synth
+    return dict(dgl_ops=dgl_ops, om=om, ope=ope, sg=sg, sm=sm, ops=ops, spe=spe, synth=synth)
+
+
+NET_CLS = {"gat": "GATNet", "gcn": "GCNNet", "gin": "GINNet", "sage": "SAGENet", "spgnn": "GATPositionSPGNNNet"}
+
+
+def _device_batch(m, scans, pos_enc=None):
+    g = m["sg"].batch_from_adjs([s["adj"] for s in scans])
+    g.ndata["fvs"] = torch.from_numpy(np.concatenate([s["fvs"] for s in scans])).cuda()
+    g.ndata["fvs_out"] = torch.from_numpy(np.concatenate([s["fvs_out"] for s in scans])).cuda()
+    if pos_enc is not None:
+        g.ndata["pos_enc"] = torch.from_numpy(pos_enc).cuda()
+    return g
+
+
+def _oracle_batch(m, scans, pos_encs=None):
+    gs = []
+    for i, s in enumerate(scans):
+        og = m["dgl_ops"].graph_from_adj(s["adj"])
+        og.ndata["fvs"] = torch.from_numpy(s["fvs"])
+        if pos_encs is not None:
+            og.ndata["pos_enc"] = torch.from_numpy(pos_encs[i])
+        gs.append(og)
+    return m["dgl_ops"].batch(gs)
+
+
+def _scan_dicts(m, first, count, ragged=True, fv_dim=1024):
+    return [dict(adj=s.adj, fvs=s.fvs, fvs_out=s.fvs_out, labels=s.labels)
+            for s in m["synth"].make_scans(first, count, ragged=ragged, fv_dim=fv_dim)]
+
+
+# ------------------------------------------------------------------------------------------------ graph
+def test_batch_builder_matches_reference_fixture(mods):
+    rec, scans = golden_graph_inputs()
+    g = _device_batch(mods, scans)
+    assert np.array_equal(g.src.cpu().numpy(), rec["b_src"])
+    assert np.array_equal(g.dst.cpu().numpy(), rec["b_dst"])
+    assert np.array_equal(g.batch_num_nodes().cpu().numpy(), rec["b_num_nodes"])
+    assert np.array_equal(g.batch_num_edges().cpu().numpy(), rec["b_num_edges"])
+    assert g.batch_size == len(scans) and g.number_of_nodes() == int(rec["b_num_nodes"].sum())
+    # dgl.batch of single graphs built one by one gives the same thing
+    singles = [mods["sg"].from_adj(s["adj"]) for s in scans]
+    for i, h in enumerate(singles):
+        assert np.array_equal(h.src.cpu().numpy(), rec[f"src{i}"]) and np.array_equal(h.dst.cpu().numpy(), rec[f"dst{i}"])
+    g2 = mods["sg"].batch(singles)
+    assert torch.equal(g2.src, g.src) and torch.equal(g2.dst, g.dst) and torch.equal(g2.in_src, g.in_src)
+
+
+def test_batch_builder_csc_csr_consistency_ragged_64(mods):
+    scans = _scan_dicts(mods, 0, 64, ragged=True, fv_dim=4)
+    g = mods["sg"].batch_from_adjs([s["adj"] for s in scans])
+    og = _oracle_batch(mods, [dict(s, fvs=s["fvs"]) for s in scans])
+    src, dst = g.src.cpu(), g.dst.cpu()
+    assert torch.equal(src, og.src) and torch.equal(dst, og.dst)
+    in_ptr, in_src, in_eid = g.in_ptr.cpu().long(), g.in_src.cpu().long(), g.in_eid.cpu().long()
+    # in-CSC: stable counting sort of the edge list by destination
+    order = torch.sort(dst, stable=True)[1]
+    assert torch.equal(in_eid, order) and torch.equal(in_src, src[order])
+    assert torch.equal(in_ptr[1:] - in_ptr[:-1], torch.bincount(dst, minlength=g.num_nodes))
+    # out-CSR: every slot appears once, grouped by source, dst consistent
+    out_ptr, out_dst, out_slot = g.out_ptr.cpu().long(), g.out_dst.cpu().long(), g.out_slot.cpu().long()
+    assert torch.equal(torch.sort(out_slot)[0], torch.arange(g.num_edges))
+    owner = torch.repeat_interleave(torch.arange(g.num_nodes), out_ptr[1:] - out_ptr[:-1])
+    assert torch.equal(in_src[out_slot], owner)
+    assert torch.equal(out_dst, dst[in_eid[out_slot]])
+    assert torch.equal(g.node_gid.cpu().long(),
+                       torch.repeat_interleave(torch.arange(64), g.batch_num_nodes().cpu()))
+
+
+def test_graph_errors(mods):
+    sg = mods["sg"]
+    from spgnn_b200._lib import SpgnnError
+    g = sg.from_edges([0, 1], [1, 2], 3)                     # node 0 has no in-edge
+    net = mods["sm"].GAT(1, 8, [8], 8, [1, 1], torch.nn.functional.elu, 0, 0, 0.2, True).cuda()
+    with pytest.raises(SpgnnError):
+        net(g, torch.zeros(3, 8, device="cuda"))
+    with pytest.raises(SpgnnError):
+        sg.from_edges([0, 5], [1, 2], 3)                     # endpoint outside the graph
+    with pytest.raises(SpgnnError):
+        mods["ops"].linear(torch.zeros(4, 4), torch.zeros(4, 4))   # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------------ projection
+@pytest.mark.parametrize("M,K1,K2,N", [(300, 64, 0, 48), (1000, 1024, 39, 130), (257, 39, 0, 258), (513, 100, 7, 22)])
+def test_linear_fwd_bwd_against_fp64(mods, M, K1, K2, N):
+    ops = mods["ops"]
+    gen = torch.Generator().manual_seed(M + N)
+    x1 = torch.randn(M, K1, generator=gen)
+    x2 = torch.randn(M, K2, generator=gen) if K2 else None
+    W = torch.randn(N, K1 + K2, generator=gen) / (K1 + K2) ** 0.5
+    b = torch.randn(N, generator=gen)
+    go = torch.randn(M, N, generator=gen)
+    xs = [t.cuda().requires_grad_() for t in ([x1, x2] if K2 else [x1])]
+    Wc, bc = W.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y = ops.linear(xs[0], Wc, bc, "elu", x2=xs[1] if K2 else None)
+    y.backward(go.cuda())
+    xd = [t.double().requires_grad_() for t in ([x1, x2] if K2 else [x1])]
+    Wd, bd = W.double().requires_grad_(), b.double().requires_grad_()
+    yd = torch.nn.functional.elu(torch.cat(xd, 1) @ Wd.t() + bd)
+    yd.backward(go.double())
+    assert rel_err(y.detach().cpu(), yd.detach()) < 1e-5
+    for a, r in zip(xs + [Wc, bc], xd + [Wd, bd]):
+        assert rel_err(a.grad.cpu(), r.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ models
+@pytest.mark.parametrize("name", sorted(TINY_MODELS))
+def test_models_match_reference_wiring_fixtures(mods, name):
+    """CUDA path vs outputs of the reference's own models.py classes (tests/golden/wiring_*.npz)."""
+    rec, scans = golden_graph_inputs()
+    w = load_golden(f"wiring_{name}.npz")
+    kind, cfg = TINY_MODELS[name]
+    net = getattr(mods["sm"], NET_CLS[kind])(**cfg).cuda()
+    res = net.load_state_dict(golden_state_dict(w), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    net.eval()
+    g = _device_batch(mods, scans, rec["b_pos_enc"])
+    with torch.no_grad():
+        out = net(g)
+    j = 0
+    while f"out{j}" in w:
+        assert rel_err(out[j].cpu(), w[f"out{j}"]) < TOL, (name, j)
+        j += 1
+    assert j == len(out)
+    dec = mods["ops"].segmented_argmax(out[0], g)
+    assert np.array_equal(dec.cpu().numpy(), w["decision"])
+    assert np.array_equal(out[0].argmax(1).cpu().numpy(), w["out0"].argmax(1))
+
+
+def _margin_aware_flips(a, b, tol):
+    """arg-max flips whose top-2 margin in the reference exceeds the tolerance (must be zero)."""
+    a, b = a.double(), b.double()
+    flips = (a.argmax(1) != b.argmax(1)).nonzero().flatten()
+    top2 = b.topk(2, dim=1)[0]
+    margin = (top2[:, 0] - top2[:, 1]) / b.abs().max()
+    return int((margin[flips] > tol).sum())
+
+
+@pytest.mark.parametrize("name", sorted(FULL_MODELS))
+def test_full_width_forward_backward_vs_oracle(mods, name):
+    """exp_settings widths, 6 ragged trees, eval-mode forward + all parameter gradients vs the CPU oracle."""
+    kind, cfg = FULL_MODELS[name]
+    scans = _scan_dicts(mods, 1000, 6, ragged=True)
+    pos = None
+    if kind == "spgnn":
+        pos = []
+        for s in scans:
+            anc = mods["ope"].anchors_39(s["fvs_out"], s["adj"])
+            pos.append(mods["ope"].dist_pos_enc(s["adj"], anc)[0])
+    torch.manual_seed(0)
+    onet = mods["om"].GNNNet(kind, cfg)
+    onet.init_like_reference()
+    with torch.no_grad():
+        for k, p in onet.named_parameters():
+            if k.endswith("bias"):
+                p.normal_(0, 0.05)
+    onet.eval()
+    net = getattr(mods["sm"], NET_CLS[kind])(**cfg).cuda()
+    net.load_state_dict(onet.state_dict(), strict=True)
+    net.eval()
+    og = _oracle_batch(mods, scans, pos)
+    g = _device_batch(mods, scans, np.concatenate(pos) if pos is not None else None)
+    y = torch.from_numpy(np.concatenate([s["labels"] for s in scans]))
+    cw = torch.tensor([0.2] + [0.8] * 21)
+    mask = torch.from_numpy(np.concatenate([s["labels"] for s in scans]) != 0) | (torch.rand(y.numel(), generator=torch.Generator().manual_seed(1)) < 0.15)
+
+    ref = onet(og)
+    loss_ref = mods["om"].cross_entropy_masked(ref[0], y, mask, cw)
+    loss_ref.backward()
+    out = net(g)
+    loss = mods["ops"].masked_cross_entropy(out[0], y.cuda(), cw.cuda(), mask=mask.cuda())
+    loss.backward()
+
+    for j in range(len(ref)):
+        assert rel_err(out[j].detach().cpu(), ref[j].detach()) < TOL, (name, "output", j)
+    assert abs(loss.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
+    assert _margin_aware_flips(out[0].detach().cpu(), ref[0].detach(), TOL) == 0
+    dec = mods["ops"].segmented_argmax(out[0].detach(), g).cpu()
+    dec_ref = mods["om"].decide_per_tree(ref[0].detach(), og.batch_num_nodes())
+    assert torch.equal(dec, dec_ref)
+    ograds = dict(onet.named_parameters())
+    for k, p in net.named_parameters():
+        r = ograds[k].grad
+        if r is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        assert rel_err(p.grad.cpu(), r) < GRAD_TOL, (name, k, rel_err(p.grad.cpu(), r))
+
+
+def test_state_dict_keys_are_dgl_names(mods):
+    kind, cfg = FULL_MODELS["st_pgat_spgnn_3"]
+    net = mods["sm"].GATPositionSPGNNNet(**cfg)
+    keys = set(net.state_dict())
+    for k in ("gat.gat_layers.0.fc.weight", "gat.gat_layers.0.attn_l", "gat.gat_layers.0.attn_r",
+              "gat.gat_layers.0.res_fc.weight", "gat.gat_layers.0.bias", "gat.pgnn_layers.2.fc.weight",
+              "gnn_out.weight", "gnn_out.bias"):
+        assert k in keys
+    assert sum(p.numel() for p in net.parameters()) == 2_501_078        # SURVEY.md §8a parameter count
+    assert tuple(net.state_dict()["gat.gat_layers.0.fc.weight"].shape) == (512, 1063)
+
+
+# ------------------------------------------------------------------------------------------------ dropout
+def test_train_mode_dropout_statistics_and_determinism(mods):
+    ops = mods["ops"]
+    x = torch.ones(2000, 64, device="cuda", requires_grad=True)
+    ops.manual_seed(7)
+    y = ops.concat_dropout(x, None, 0.1, True)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.01 and abs(y.mean().item() - 1.0) < 0.02
+    assert torch.all((y == 0) | ((y - 1 / 0.9).abs() < 1e-6))
+    y.sum().backward()
+    assert torch.equal((x.grad != 0), (y != 0))             # backward regenerates the same mask
+    ops.manual_seed(7)
+    assert torch.equal(ops.concat_dropout(x, None, 0.1, True), y)
+
+    kind, cfg = TINY_MODELS["spgnn3"]
+    rec, scans = golden_graph_inputs()
+    net = mods["sm"].GATPositionSPGNNNet(**cfg).cuda()
+    g = _device_batch(mods, scans, rec["b_pos_enc"])
+    net.train()
+    ops.manual_seed(3)
+    a = net(g)[0]
+    ops.manual_seed(3)
+    b = net(g)[0]
+    ops.manual_seed(4)
+    c = net(g)[0]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    net.eval()
+    assert not torch.equal(net(g)[0], a)
+
+
+# ------------------------------------------------------------------------------------------------ PE
+def test_anchor_select_and_distance_pe_match_reference_fixture(mods):
+    rec, scans = golden_graph_inputs()
+    g = _device_batch(mods, scans)
+    anc = mods["spe"].select_anchors(g).cpu().numpy()
+    for i, s in enumerate(scans):
+        ref = rec[f"anchors{i}"]
+        assert np.array_equal(anc[i, :21], ref[:21])                       # CNN anchors: exact
+        assert anc[i].tolist() == mods["ope"].anchors_39(s["fvs_out"], s["adj"])     # distal leaves: deterministic rule
+    # with the reference's anchors the encoding is bit-identical to the reference's
+    ref_anc = torch.from_numpy(np.stack([rec[f"anchors{i}"] for i in range(len(scans))])).int().cuda()
+    pe, diam = mods["spe"].distance_pos_enc(g, ref_anc)
+    assert np.array_equal(pe.cpu().numpy(), rec["b_pos_enc"])
+    for i, s in enumerate(scans):
+        assert int(diam[i]) == mods["ope"].dist_pos_enc(s["adj"], rec[f"anchors{i}"].tolist())[2]
+
+
+def test_pe_on_64_ragged_trees_vs_oracle(mods):
+    scans = _scan_dicts(mods, 500, 64, ragged=True, fv_dim=4)
+    g = _device_batch(mods, scans)
+    anc = mods["spe"].select_anchors(g)
+    pe, _ = mods["spe"].distance_pos_enc(g, anc)
+    rw = mods["spe"].rw_pos_enc(g)
+    anc, pe, rw = anc.cpu().numpy(), pe.cpu().numpy(), rw.cpu().numpy()
+    off = g.node_off.cpu().numpy()
+    for i, s in enumerate(scans):
+        ref_anc = mods["ope"].anchors_39(s["fvs_out"], s["adj"])
+        assert anc[i].tolist() == ref_anc
+        assert np.array_equal(pe[off[i]:off[i + 1]], mods["ope"].dist_pos_enc(s["adj"], ref_anc)[0])
+    for i in (0, 17, 63):
+        ref = mods["ope"].rw_pos_enc(scans[i]["adj"], 39)
+        got = rw[off[i]:off[i + 1]]
+        assert np.all(got[:, 0::2] == 0)
+        assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
+        assert np.allclose(got, ref, rtol=TOL, atol=1e-12)
+
+
+def test_rw_pe_matches_reference_fixture(mods):
+    rec, scans = golden_graph_inputs()
+    g = _device_batch(mods, scans)
+    rw = mods["spe"].rw_pos_enc(g).cpu().numpy()
+    off = g.node_off.cpu().numpy()
+    for i in range(len(scans)):
+        assert np.allclose(rw[off[i]:off[i + 1]], rec[f"rw_enc{i}"], rtol=TOL, atol=1e-12)
+
+
+def test_disconnected_graph_raises(mods):
+    from spgnn_b200._lib import SpgnnError
+    adj = np.eye(30, dtype=np.uint8)
+    adj[0, 1] = adj[1, 0] = 1
+    g = mods["sg"].from_adj(adj)
+    with pytest.raises(SpgnnError):
+        mods["spe"].distance_pos_enc(g, torch.zeros(1, 39, dtype=torch.int32, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------ loss / decision
+def test_masked_ce_on_device_mask(mods):
+    ops = mods["ops"]
+    N = 5000
+    gen = torch.Generator().manual_seed(0)
+    logits = torch.randn(N, 22, generator=gen)
+    y = torch.where(torch.rand(N, generator=gen) < 0.07, torch.randint(1, 22, (N,), generator=gen), torch.zeros(N, dtype=torch.long))
+    cw = torch.tensor([0.2] + [0.8] * 21)
+    lc = logits.cuda().requires_grad_()
+    loss = ops.masked_cross_entropy(lc, y.cuda(), cw.cuda(), rate=0.15, seed=99)
+    loss.backward()
+    kept = lc.grad.abs().sum(1) != 0
+    assert torch.all(kept[y.cuda() != 0])                                 # every labelled node survives (job_runner.py:1897)
+    frac = kept[y.cuda() == 0].float().mean().item()
+    assert abs(frac - 0.15) < 0.02
+    lr = logits.clone().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(lr[kept.cpu()], y[kept.cpu()], weight=cw)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_err(lc.grad.cpu(), lr.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ device generator
+def test_device_synth_integer_part_is_bit_identical_to_host(mods):
+    from spgnn_b200 import synth_device
+    for ragged in (False, True):
+        scans = mods["synth"].make_scans(40, 8, ragged=ragged, fv_dim=8)
+        b = synth_device.make_batch(40, 8, ragged=ragged, fv_dim=8, features=True)
+        off = b.graph.node_off.cpu().numpy()
+        for i, s in enumerate(scans):
+            assert np.array_equal(b.parent[off[i]:off[i + 1]].cpu().numpy(), s.parent)
+            assert np.array_equal(b.graph.ndata["y"][off[i]:off[i + 1]].cpu().numpy(), s.labels)
+            assert np.allclose(b.graph.ndata["fvs"][off[i]:off[i + 1]].cpu().numpy(), s.fvs, atol=2e-5)
+            assert np.allclose(b.graph.ndata["fvs_out"][off[i]:off[i + 1]].cpu().numpy(), s.fvs_out, atol=1e-4)
+        ref = mods["sg"].batch_from_adjs([s.adj for s in scans])
+        assert torch.equal(ref.src, b.graph.src) and torch.equal(ref.dst, b.graph.dst)
