@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kPeThreads) anchor_select_kernel(const float* 
     float* inv = mx + max_nodes;
     unsigned char* mask = reinterpret_cast<unsigned char*>(inv + max_nodes);
     unsigned char* leaf = mask + max_nodes;
-    int16_t* dist = reinterpret_cast<int16_t*>(leaf + max_nodes + (max_nodes & 1));
+    int16_t* dist = reinterpret_cast<int16_t*>(leaf + max_nodes);   // byte offset 10*max_nodes: even
     const int n_labels = C - 1;   // 21
 
     for (int v = threadIdx.x; v < n; v += blockDim.x) {

@@ -200,13 +200,19 @@ def test_full_width_forward_backward_vs_oracle(mods, name):
     dec_ref = mods["om"].decide_per_tree(ref[0].detach(), og.batch_num_nodes())
     assert torch.equal(dec, dec_ref)
     ograds = dict(onet.named_parameters())
+    # Gradients that are analytically ~0 (e.g. d attn_r: the softmax is shift-invariant in er, only the LeakyReLU
+    # kink lets anything through) are pure fp32 cancellation noise in BOTH implementations; they are held to an
+    # absolute floor of 1e-6 x the largest gradient in the model instead of a relative bar against noise.
+    gmax = max(float(q.grad.abs().max()) for q in ograds.values() if q.grad is not None)
     for k, p in net.named_parameters():
         r = ograds[k].grad
         if r is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert p.grad is not None, k
-        assert rel_err(p.grad.cpu(), r) < GRAD_TOL, (name, k, rel_err(p.grad.cpu(), r))
+        abs_err = float((p.grad.cpu().double() - r.double()).abs().max())
+        assert abs_err <= GRAD_TOL * float(r.abs().max()) or abs_err <= 1e-6 * gmax, \
+            (name, k, rel_err(p.grad.cpu(), r), abs_err, gmax)
 
 
 def test_state_dict_keys_are_dgl_names(mods):
