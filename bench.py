@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Headline benchmark: SPGNN-3 (st_pgat_spgnn_3) training step on synthetic airway-tree batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--trees B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one iteration of the reference's GCN_STEPS loop (job_runner.py:1892-1919) over one batch of B trees
+per GPU: zero_grad, forward (7 GATConv + head, train mode with dropout), masked weighted CE, backward,
+gradient all-reduce (N > 1) and the SGD-momentum update.  Prints ONE JSON line (rank 0).
+
+  value     graphs/s, whole job, batch resident in HBM (CUDA events, max over ranks)
+  e2e       graphs/s through the public API from pinned HOST buffers: H2D of adj/fvs/fvs_out/labels, device graph
+            build + positional encoding + the training step, D2H of the loss — every step
+  roofline  dominant kernel by time share, algorithmic flops (or bytes) per launch / CUDA-event duration
+  cpu_baseline  the oracle (PyTorch-CPU restatement of the DGL op sequence; DGL itself is not installable) on
+            a bounded sample of the same workload, on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = dict(out_ch=22, fv_dim=1024, num_hiddens=[256, 128, 64], node_embed_dim=1024, num_gat_layers=3, num_heads=2,
+             num_out_heads=2, feat_drop=0.1, attn_drop=0.1, negative_slope=0.2, pos_hiddens=[256, 128, 64],
+             num_pos_heads=1, pos_enc_dim=39)          # exp_settings/st_pgat_spgnn_3.py:85-116 (GNN keys)
+SAMPLING_RATE = 0.15                                   # st_pgat_spgnn_3.py:79
+LR, MOMENTUM = 5e-4, 0.9                               # train.py:14 default lr; st_pgat_spgnn_3.py:124-128
+SEED = 1234
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        mx = max((int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_rate(trees, steps, warmup, threads):
+    """graphs/s of the CPU oracle on SPGNN-3 fwd+bwd+SGD over `trees` synthetic trees (same generator, same model)."""
+    import numpy as np
+    import torch
+    from oracle import dgl_ops, models as om, pe as ope
+    from spgnn_b200 import synth
+    torch.set_num_threads(threads)
+    scans = synth.make_scans(0, trees, seed=SEED)
+    gs = []
+    for s in scans:
+        g = dgl_ops.graph_from_adj(s.adj)
+        g.ndata["fvs"] = torch.from_numpy(s.fvs)
+        anc = ope.anchors_39(s.fvs_out, s.adj)
+        g.ndata["pos_enc"] = torch.from_numpy(ope.dist_pos_enc(s.adj, anc)[0])
+        gs.append(g)
+    bg = dgl_ops.batch(gs)
+    y = torch.from_numpy(np.concatenate([s.labels for s in scans]))
+    torch.manual_seed(0)
+    net = om.GNNNet("spgnn", MODEL)
+    net.init_like_reference()
+    net.train()
+    opt = torch.optim.SGD(net.parameters(), lr=LR, momentum=MOMENTUM)
+    cw = torch.tensor([0.2] + [0.8] * 21)
+    gen = torch.Generator().manual_seed(0)
+
+    def step():
+        opt.zero_grad()
+        mask = (y != 0) | (torch.rand(y.numel(), generator=gen) < SAMPLING_RATE)
+        out = net(bg)
+        loss = om.cross_entropy_masked(out[0], y, mask, cw)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return trees / dt, dt, int(bg.num_nodes)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle restatement; DGL is not installable) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    trees = args.cpu_trees
+    rate, dt, nodes = cpu_oracle_rate(trees, max(1, args.steps), max(1, min(args.warmup, 2)), cores)
+    line = {
+        "impl": "reference", "metric": "spgnn3_train_graphs_per_s", "value": rate, "unit": "graphs/s",
+        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "nodes_per_s": rate * nodes / trees,
+        "config": {"workload": "st_pgat_spgnn_3 train step (fwd+bwd+SGD), synthetic bifurcating airway trees n=301",
+                   "trees_per_step": trees, "nodes_per_step": nodes},
+        "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
+                         "sample": f"{trees} trees/step (bounded sample of the 4096-tree batch); oracle = PyTorch-CPU "
+                                   f"restatement of the DGL-0.7 op sequence, torch threads = {cores}"},
+        "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spgnn_b200 import models as sm, ops, pe as spe, runner, synth_device
+    from spgnn_b200._lib import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gemm_mode is not None:
+        ops.GEMM_MODE = args.gemm_mode
+    B = args.trees
+    L = lib()
+
+    # -------- synthetic batch on device (this rank's shard of the global batch), positional encoding on device
+    batch = synth_device.make_batch(first_tree=rank * B, count=B, seed=SEED)
+    g = batch.graph
+    spe.distance_pos_enc(g, pos_enc_dim=MODEL["pos_enc_dim"])
+    N, E = g.num_nodes, g.num_edges
+
+    torch.manual_seed(0)
+    net = sm.GATPositionSPGNNNet(**MODEL).to(dev)
+    net.init()
+    net.train()
+    net.set_gcn_only()
+    opt = runner.FlatSGD(net.parameters(), lr=LR, momentum=MOMENTUM)
+    cw = torch.tensor(runner.CLASS_WEIGHTS_22, device=dev)
+    ops.manual_seed(SEED)
+
+    def step():
+        return runner.train_step(net, g, opt, cw, SAMPLING_RATE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (L.launch_count() - l0) // args.steps
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    loss_val = float(loss.item())
+
+    # -------- per-kernel profile pass (CUDA events around every C-ABI call; separate from the timed region)
+    roof, roof_agg, shares = None, None, None
+    if rank == 0:
+        L.profile = []
+        for _ in range(max(1, min(3, args.steps))):
+            step()
+        torch.cuda.synchronize()
+        prof, L.profile = L.profile, None
+        agg = {}
+        for name, key, a, b in prof:
+            d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += a.elapsed_time(b)
+            d["n"] += 1
+            if key:
+                d[key[0]] += key[1]
+        total = sum(d["ms"] for d in agg.values())
+        shares = {k: round(d["ms"] / total, 4) for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+        pk = peaks()
+
+        def roofline(name):
+            d = agg.get(name)
+            if not d or d["ms"] == 0:
+                return None
+            sec = d["ms"] / 1e3
+            if d["flops"] > 0:
+                ach = d["flops"] / sec / 1e12
+                return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                        "frac": ach / pk["tf_sust"], "traffic": None, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
+                        "peak_source": pk["src"] + " bf16 dense, sustained", "share_of_step": d["ms"] / total,
+                        "note": "fp32-accurate projection; algorithmic flops 2*M*N*K"}
+            ach = d["bytes"] / sec / 1e9
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
+                    "peak_source": pk["src"] + " copy bandwidth", "share_of_step": d["ms"] / total,
+                    "frac_of_nominal_8TBs": ach / 8000.0}
+        dominant = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]
+        roof = roofline(dominant)
+        roof_agg = {"fwd": roofline("gat_agg_fwd"), "bwd": roofline("gat_agg_bwd")}
+
+    # -------- end to end through the public API from pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        hb = runner.host_batch_from_graph(g)
+        h2d = hb.nbytes()
+        barrier()
+
+        def e2e_step():
+            gg = runner.batch_to_device(hb, pos_enc_dim=MODEL["pos_enc_dim"], device=dev)
+            ls = runner.train_step(net, gg, opt, cw, SAMPLING_RATE)
+            return float(ls.item())                      # D2H read of the loss
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B / float(t.item()), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": float(t.item()) * 1e3, "steps": args.e2e_steps}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        rate, dt, nodes = cpu_oracle_rate(args.cpu_trees, 2, 1, cores)
+        cpu = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_trees} trees/step x 2 steps (+1 warm-up) of the same SPGNN-3 train step; oracle = "
+                         f"PyTorch-CPU restatement of the DGL-0.7 op sequence (DGL not installable), {cores} threads",
+               "ms_per_step": dt * 1e3}
+
+    if rank == 0:
+        gps = world * B / (ms / 1e3)
+        line = {
+            "metric": "spgnn3_train_graphs_per_s", "value": gps, "unit": "graphs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "nodes_per_s": gps * N / B,
+            "config": {"workload": "st_pgat_spgnn_3 train step (fwd+bwd+SGD), synthetic bifurcating airway trees n=301",
+                       "trees_per_gpu": B, "nodes_per_gpu": N, "edges_per_gpu": E, "parallelism": f"dp{world} by graph",
+                       "l2": "inputs (5.2 GB/GPU) larger than L2, no flush needed", "gemm_mode": ops.GEMM_MODE,
+                       "loss": loss_val},
+            "roofline": roof, "roofline_agg": roof_agg, "kernel_time_shares": shares,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--trees", type=int, default=4096, help="trees per GPU per step (BASELINE config 2)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-trees", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gemm-mode", type=int, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ extern "C" {
 
 const char* spgnn_last_error(void);
 int  spgnn_abi_version(void);
+/* Number of kernels this library has launched in this process (diagnostic counter; bench.py's gpu_launches). */
+int64_t spgnn_launch_count(void);
 /* SM count etc. of the current device (used by the host side to size workspaces). */
 int  spgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

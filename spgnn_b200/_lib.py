@@ -61,6 +61,7 @@ class _Lib:
             fn.argtypes = argtypes
         self._status = {n for n, r, _ in self.protos if r is ctypes.c_int and n not in
                         ("spgnn_abi_version",)}
+        self.profile = None          # when a list: (name, key, start_event, stop_event) per C-ABI call
 
     def last_error(self):
         return self._dll.spgnn_last_error().decode()
@@ -70,10 +71,17 @@ class _Lib:
         if "spgnn_" + name not in self._status:
             return fn
 
-        def call(*args):
+        def call(*args, _key=None):
+            prof = self.profile
+            if prof is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = fn(*args)
             if rc != 0:
                 raise SpgnnError(f"spgnn_{name} failed ({rc}): {self.last_error()}")
+            if prof is not None:
+                e1.record()
+                prof.append((name, _key, e0, e1))
         return call
 
 

@@ -10,6 +10,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -26,6 +29,7 @@ int sm_count() {
 
 extern "C" const char* spgnn_last_error(void) { return spgnn::g_err; }
 extern "C" int spgnn_abi_version(void) { return 1; }
+extern "C" int64_t spgnn_launch_count(void) { return (int64_t)spgnn::launches(); }
 extern "C" int spgnn_device_info(int* sm, int* major, int* minor) {
     int dev = 0;
     SPGNN_CUDA_OK(cudaGetDevice(&dev));

@@ -9,6 +9,7 @@
 namespace spgnn {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define SPGNN_REQUIRE(cond, ...)                               \
     do {                                                       \
@@ -27,7 +28,12 @@ void set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
-#define SPGNN_LAUNCH_OK() SPGNN_CUDA_OK(cudaGetLastError())
+// every kernel launch goes through this: counts launches (bench.py's gpu_launches) and checks the launch status
+#define SPGNN_LAUNCH_OK()                      \
+    do {                                       \
+        spgnn::count_launch();                 \
+        SPGNN_CUDA_OK(cudaGetLastError());     \
+    } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

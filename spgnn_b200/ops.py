@@ -81,7 +81,8 @@ class LinearFn(Function):
         y = empty_padded(M, N, x1.device)
         b = bias.contiguous() if bias is not None else None
         lib().linear_fwd(ptr(x1), x1.stride(0), K1, ptr(x2), x2.stride(0) if x2 is not None else 0, K2,
-                         ptr(W), W.stride(0), ptr(b), act, float(slope), ptr(y), y.stride(0), M, N, GEMM_MODE, stream())
+                         ptr(W), W.stride(0), ptr(b), act, float(slope), ptr(y), y.stride(0), M, N, GEMM_MODE, stream(),
+                         _key=("flops", 2.0 * M * N * (K1 + K2)))
         ctx.save_for_backward(x1, x2, W, y if act else None)
         ctx.cfg = (act, float(slope), bias is not None)
         return y
@@ -103,11 +104,11 @@ class LinearFn(Function):
         if ctx.needs_input_grad[0]:
             dx1 = empty_padded(M, K1, g.device)
             L.linear_bwd_input(ptr(g), g.stride(0), ptr(W), W.stride(0), 0, ptr(dx1), dx1.stride(0), M, N, K1,
-                               GEMM_MODE, stream())
+                               GEMM_MODE, stream(), _key=("flops", 2.0 * M * N * K1))
         if x2 is not None and ctx.needs_input_grad[1]:
             dx2 = empty_padded(M, K2, g.device)
             L.linear_bwd_input(ptr(g), g.stride(0), ptr(W), W.stride(0), K1, ptr(dx2), dx2.stride(0), M, N, K2,
-                               GEMM_MODE, stream())
+                               GEMM_MODE, stream(), _key=("flops", 2.0 * M * N * K2))
         if ctx.needs_input_grad[2]:
             dW = empty_padded(N, K1 + K2, g.device)
             for x, koff, K in ((x1, 0, K1), (x2, K1, K2)):
@@ -115,7 +116,7 @@ class LinearFn(Function):
                     continue
                 ws = torch.empty(max(int(L.linear_bwd_weight_ws(M, N, K)), 16), dtype=torch.uint8, device=g.device)
                 L.linear_bwd_weight(ptr(g), g.stride(0), ptr(x), x.stride(0), ptr(dW), dW.stride(0), koff, M, N, K,
-                                    ptr(ws), GEMM_MODE, stream())
+                                    ptr(ws), GEMM_MODE, stream(), _key=("flops", 2.0 * M * N * K))
         if has_bias and ctx.needs_input_grad[3]:
             db = colsum(g)
         return dx1, dx2, dW, db, None, None
@@ -208,7 +209,9 @@ class GatAggFn(Function):
         lib().gat_agg_fwd(ptr(Y), Y.stride(0), res_off, el_off, er_off, res_mode, ptr(xr),
                           xr.stride(0) if xr is not None else 0, xr.shape[1] if xr is not None else 0, ptr(b), act,
                           float(neg_slope), int(mean_heads), float(drop_p), seed, ptr(graph.in_ptr), ptr(graph.in_src),
-                          N, H, F, ptr(out), out.stride(0), ptr(att), stream())
+                          N, H, F, ptr(out), out.stride(0), ptr(att), stream(),
+                          _key=("bytes", 4.0 * N * (HF + (HF if res_mode == 1 else 0) + 2 * H + (F if mean_heads else HF))
+                                + 4.0 * (N + 1) + 4.0 * graph.num_edges))
         ctx.save_for_backward(Y, xr, b, out if not mean_heads else None, att)
         ctx.graph = graph
         ctx.cfg = (H, F, res_mode, act, float(neg_slope), int(mean_heads), float(drop_p), seed, res_off, el_off, er_off)
@@ -230,7 +233,9 @@ class GatAggFn(Function):
                           res_off, el_off, er_off, res_mode, ptr(xr), xr.stride(0) if xr is not None else 0,
                           xr.shape[1] if xr is not None else 0, ptr(b), act, neg_slope, mean_heads, drop_p, seed,
                           ptr(att), ptr(gr.in_ptr), ptr(gr.in_src), ptr(gr.out_ptr), ptr(gr.out_dst), ptr(gr.out_slot),
-                          N, H, F, ptr(dY), ptr(dxres), ptr(g_ws), ptr(ds), stream())
+                          N, H, F, ptr(dY), ptr(dxres), ptr(g_ws), ptr(ds), stream(),
+                          _key=("bytes", 4.0 * N * ((F if mean_heads else 2 * HF) + 2 * (Y.shape[1]))
+                                + 8.0 * (N + 1) + 12.0 * gr.num_edges))
         db = None
         if b is not None and ctx.needs_input_grad[2]:
             db = colsum(dY[:, res_off:res_off + HF] if res_mode == 1 else g_ws)

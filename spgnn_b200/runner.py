@@ -1,0 +1,127 @@
+"""Callers of the hot path, kept on device: batch assembly from host buffers, the training step of
+/root/reference/job_runner.py:1863-1920 (GCNTrainSPGNN.train) / :1368-1416 (GCNTrain.train) and the SGD update.
+
+One process per GPU; trees shard by graph (they are independent components): inference needs no
+collective, training adds ONE NCCL all-reduce of the flat gradient bucket per step, and the masked weighted
+cross-entropy is normalised by the GLOBAL Σw so that G-GPU training equals one big batch (sum order aside).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import graph as sg, ops, pe as spe
+from ._lib import lib, ptr, stream
+
+CLASS_WEIGHTS_22 = [0.2] + [0.8] * 21      # exp_settings/st_pgat_spgnn_3.py:70-74 via job_runner.py:1867
+
+
+class FlatSGD:
+    """torch.optim.SGD(momentum) semantics over ONE flat fp32 bucket: parameters and gradients are views into two
+    contiguous buffers, so a step is one all-reduce (when world_size > 1) plus one fused update kernel."""
+
+    def __init__(self, params, lr, momentum=0.9, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr, self.momentum = float(lr), float(momentum)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.buf = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + k].view_as(p.data)
+            p.grad = self.flat_g[o:o + k].view_as(p.data)
+            o += k
+        self.steps = 0
+        self.numel = n
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def step(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        lib().sgd_momentum(ptr(self.flat_p), ptr(self.flat_g), ptr(self.buf), self.numel, self.lr, self.momentum, 1.0,
+                           int(self.steps == 0), stream())
+        self.steps += 1
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+
+
+def _allreduce_sums(group=None):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+
+    def fn(sums):
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        return sums
+    return fn
+
+
+def train_step(net, g, opt, class_w, sampling_rate, mask=None, group=None):
+    """One iteration of the reference's GCN_STEPS loop (job_runner.py:1892-1919): zero_grad, forward, masked
+    weighted CE (labelled nodes always kept, label-0 nodes with probability ``sampling_rate``), backward, step."""
+    opt.zero_grad()
+    out = net(g)
+    loss = ops.masked_cross_entropy(out[0], g.ndata["y"], class_w, mask=mask, rate=sampling_rate,
+                                    reduce_fn=_allreduce_sums(group))
+    loss.backward()
+    opt.step()
+    return loss
+
+
+@torch.no_grad()
+def infer(net, g):
+    """GCNTestSPGNN.run's device part (job_runner.py:2052 + :158-165): logits → per-tree per-class arg-max node."""
+    out = net(g)
+    return out[0], ops.segmented_argmax(out[0], g)
+
+
+class HostBatch:
+    """A batch of scans in (pinned) host memory, in the stage-1 pickle layout concatenated over scans
+    (job_runner.py:796-805): adj uint8 blocks, fvs fp32 [N,1024], fvs_out fp32 [N,22], labels int64 [N]."""
+
+    def __init__(self, n_nodes, adj_cat, fvs, fvs_out, labels, pin=True):
+        f = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+        self.n_nodes = f(torch.as_tensor(n_nodes, dtype=torch.int64))
+        self.adj_cat, self.fvs, self.fvs_out, self.labels = f(adj_cat), f(fvs), f(fvs_out), f(labels)
+        self.max_nodes = int(self.n_nodes.max())
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.n_nodes, self.adj_cat, self.fvs, self.fvs_out, self.labels))
+
+
+def batch_to_device(hb: HostBatch, pos_enc_dim=39, device=None, pe_kind="dist"):
+    """Host buffers → device graph batch with features and positional encoding: the per-batch part of
+    GCNTrainSPGNN.train (job_runner.py:1872-1882) — H2D copies, from_adj_to_graph for every scan, PE, dgl.batch."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    n_nodes = hb.n_nodes.to(dev, non_blocking=True)
+    adj = hb.adj_cat.to(dev, non_blocking=True)
+    fvs = hb.fvs.to(dev, non_blocking=True)
+    fvs_out = hb.fvs_out.to(dev, non_blocking=True)
+    labels = hb.labels.to(dev, non_blocking=True)
+    n_edges, sl, dl = sg._edges_from_dense(adj, n_nodes, dev)
+    g = sg.Graph.from_edge_lists(n_nodes, n_edges, sl, dl, max_nodes=hb.max_nodes, check=False)
+    g.ndata["fvs"], g.ndata["fvs_out"], g.ndata["y"] = fvs, fvs_out, labels
+    if pos_enc_dim:
+        if pe_kind == "dist":
+            spe.distance_pos_enc(g, pos_enc_dim=pos_enc_dim)
+        else:
+            g.ndata["pos_enc"] = spe.rw_pos_enc(g, pos_enc_dim)
+    return g
+
+
+def host_batch_from_graph(g, pin=True):
+    """Device batch → HostBatch (bench/test helper: produces the host-side inputs of the end-to-end path)."""
+    n = g.batch_num_nodes()
+    adj_off = sg.device_scan(n * n)
+    adj = torch.zeros(int(adj_off[-1].item()), dtype=torch.uint8, device=g.device)
+    gid = torch.repeat_interleave(torch.arange(g.batch_size, device=g.device), g.batch_num_edges())
+    adj[adj_off[gid] + g.src_local * n[gid] + g.dst_local] = 1
+    return HostBatch(n.cpu(), adj.cpu(), g.ndata["fvs"].cpu(), g.ndata["fvs_out"].cpu(), g.ndata["y"].cpu(), pin=pin)
