@@ -92,14 +92,20 @@ int spgnn_batch_build(const int64_t* node_off, const int64_t* edge_off, int64_t 
  * SURVEY §2.1 K1/K8.  fp32 in, fp32 out.
  *   C[M,N] (ldc) = [A1 | A2][M,K1+K2] * W[N, K1+K2 (ldw)]^T  (+ bias[N]) (act)
  * A2 may be null (K2 = 0): the two-source form removes torch.cat([h_s,h_p]) (models.py:477,481).
- * mode: 0 = fp32 SIMT, 1 = tcgen05 bf16x3 split (error-compensated, ~2^-17 rel), -1 = library default.
+ * mode: 0 = fp32 SIMT, 1 = tcgen05 tensor cores with split-bf16 operands (a = hi + lo; hi*hi + hi*lo + lo*hi,
+ *       fp32 accumulate in TMEM; relative error ~1e-5) — falls back to mode 0 when 16-byte alignment of the
+ *       operands / leading dimensions is not given.  ws: scratch for the pre-split weight, spgnn_linear_fwd_ws /
+ *       spgnn_linear_bwd_input_ws bytes (mode 1 only).
  * ---------------------------------------------------------------------------------- */
+int64_t spgnn_linear_fwd_ws(int64_t N, int64_t K1, int64_t K2);
 int spgnn_linear_fwd(const float* A1, int64_t lda1, int64_t K1, const float* A2, int64_t lda2, int64_t K2,
                      const float* W, int64_t ldw, const float* bias, int act, float slope,
-                     float* C, int64_t ldc, int64_t M, int64_t N, int mode, void* stream);
+                     float* C, int64_t ldc, int64_t M, int64_t N, int mode, void* ws, int64_t ws_bytes, void* stream);
 /* dA[M,K] (ldda) = dC[M,N] (lddc) * W[N, k_off : k_off+K] (ldw) */
+int64_t spgnn_linear_bwd_input_ws(int64_t N, int64_t K);
 int spgnn_linear_bwd_input(const float* dC, int64_t lddc, const float* W, int64_t ldw, int64_t k_off,
-                           float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K, int mode, void* stream);
+                           float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K, int mode,
+                           void* ws, int64_t ws_bytes, void* stream);
 /* dW[N, k_off : k_off+K] (lddw) = dC[M,N]^T * A[M,K] (lda); split over M into `splits` partial sums in ws
  * (splits*N*K floats, see spgnn_linear_bwd_weight_ws) that a second kernel reduces deterministically. */
 int64_t spgnn_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K);

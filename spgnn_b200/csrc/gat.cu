@@ -24,6 +24,7 @@ struct GatArgs {
     // backward
     const float* g_out; int64_t ldg; const float* out_saved; const float* att_in;
     float* dY; float* G; int64_t ldG; float* dxres; float* ds;
+    int skip_fast;   // general kernels: leave nodes with 1..4 in/out-edges to the fast kernels
 };
 
 __device__ __forceinline__ float keep_scale(const GatArgs& a, int64_t slot, int h) {
@@ -61,7 +62,7 @@ __device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(
 __device__ __forceinline__ float4 scale4(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float4 act4(float4 p, int act) {
-    return make_float4(act_fwd(p.x, act, 0.f), act_fwd(p.y, act, 0.f), act_fwd(p.z, act, 0.f), act_fwd(p.w, act, 0.f));
+    return make_float4(act_fast(p.x, act), act_fast(p.y, act), act_fast(p.z, act), act_fast(p.w, act));
 }
 __device__ __forceinline__ float4 actgrad4(float4 y, int act) {
     return make_float4(act_grad_from_out(y.x, act, 0.f), act_grad_from_out(y.y, act, 0.f),
@@ -85,6 +86,228 @@ __device__ __forceinline__ float4 pre_chunk(const GatArgs& a, const float* att, 
     return acc;
 }
 
+// Fast-path helper: attention weights (after dropout scaling) and source ids of up to 4 in-edges, warp-uniform.
+struct Edge4 {
+    int u[4];
+    float w[4];
+};
+__device__ __forceinline__ Edge4 load_edges4(const GatArgs& a, const float* att, int beg, int deg, int h) {
+    Edge4 e;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool on = j < deg;
+        e.u[j] = on ? __ldg(a.in_src + beg + j) : 0;
+        e.w[j] = on ? att[(int64_t)(beg + j) * a.H + h] * keep_scale(a, beg + j, h) : 0.f;
+    }
+    return e;
+}
+// sum_j w_j * z[u_j, h, col..col+3] with the (<= 4) row loads issued back to back
+__device__ __forceinline__ float4 gather4(const GatArgs& a, const Edge4& e, int deg, int hc) {
+    float4 z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        z[j] = j < deg ? ldg4(a.Y + (int64_t)e.u[j] * a.ldy + hc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = fma4(e.w[j], z[j], acc);
+    return acc;
+}
+__device__ __forceinline__ float4 add_res_bias(const GatArgs& a, float4 acc, int64_t v, int hc) {
+    if (a.res_mode == 1) acc = add4(acc, ldg4(a.Y + v * a.ldy + a.res_off + hc));
+    else if (a.res_mode == 2) acc = add4(acc, ldg4(a.xres + v * a.ldxres + (hc % a.xres_cols)));
+    if (a.bias) acc = add4(acc, ldg4(a.bias + hc));
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path: in-degree <= 4 and H <= 2 (every airway-tree node: <= 3 neighbours + the self loop).
+// Lanes 0..7 own one (edge j = lane & 3, head h = lane >> 2) pair for the softmax; everything is then broadcast
+// with shuffles, neighbour rows are addressed through 4 precomputed row pointers (edges beyond the degree alias the
+// last real edge with weight 0, so the row loads need no predication) and issued back to back.
+// ------------------------------------------------------------------------------------------------------------
+template <int H>
+struct Nbr4 {
+    const float* row[4];     // Y rows of the (<= 4) sources
+    float w[H][4];           // attention weights after dropout scaling, 0 beyond the degree
+    float att[H][4];         // softmax weights before dropout
+    int u[4];
+};
+
+// forward: computes the edge softmax from el/er, optionally writes att[]
+template <int H, bool kWriteAtt>
+__device__ __forceinline__ Nbr4<H> softmax4(const GatArgs& a, int64_t v, int beg, int deg, int lane, float* att_out) {
+    const int j = lane & 3, h = min((lane >> 2) & 1, H - 1);
+    const int s = beg + min(j, deg - 1);
+    const int u = __ldg(a.in_src + s);
+    const float raw = __ldg(a.Y + (int64_t)u * a.ldy + a.el_off + h) + __ldg(a.Y + v * a.ldy + a.er_off + h);
+    const float e = leaky(raw, a.neg_slope);
+    const bool valid = j < deg;
+    float m = valid ? e : -INFINITY;
+    m = fmaxf(m, __shfl_xor_sync(kFull, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(kFull, m, 2));
+    const float p = valid ? __expf(e - m) : 0.f;
+    float sum = p + __shfl_xor_sync(kFull, p, 1);
+    sum += __shfl_xor_sync(kFull, sum, 2);
+    const float att = p / sum;
+    if (kWriteAtt && valid && lane < 4 * H) att_out[(int64_t)s * H + h] = att;
+    const float w = att * keep_scale(a, s, h);
+    Nbr4<H> n;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        n.u[jj] = __shfl_sync(kFull, u, jj);
+        n.row[jj] = a.Y + (int64_t)n.u[jj] * a.ldy;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+            n.w[hh][jj] = __shfl_sync(kFull, w, jj + 4 * hh);
+            n.att[hh][jj] = __shfl_sync(kFull, att, jj + 4 * hh);
+        }
+    }
+    return n;
+}
+
+template <int H>
+__device__ __forceinline__ float4 gather_rows(const Nbr4<H>& n, int h, int hc, float4 (&z)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = ldg4(n.row[j] + hc);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = fma4(n.w[h][j], z[j], acc);
+    return acc;
+}
+
+template <int H>
+__device__ __forceinline__ void fwd_node_fast(const GatArgs& a, int64_t v, int beg, int deg, int lane) {
+    const Nbr4<H> n = softmax4<H, true>(a, v, beg, deg, lane, a.att);
+    const float inv_h = 1.f / (float)H;
+    float* orow = a.out + v * a.ldo;
+    for (int col = lane * 4; col < a.F; col += 128) {
+        float4 y[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float4 z[4];
+            y[h] = act4(add_res_bias(a, gather_rows<H>(n, h, h * a.F + col, z), v, h * a.F + col), a.act);
+        }
+        if (a.mean_heads) {
+            float4 m = y[0];
+#pragma unroll
+            for (int h = 1; h < H; ++h) m = add4(m, y[h]);
+            st4(orow + col, scale4(inv_h, m));
+        } else {
+#pragma unroll
+            for (int h = 0; h < H; ++h) st4(orow + h * a.F + col, y[h]);
+        }
+    }
+}
+
+// backward, destination side: one pass over the chunks computes g (and stores it), and the 4 x H dot products
+// <g, z[u_j]> from the SAME z registers that the (mean-mode) recomputation of the pre-activation used.
+template <int H>
+__device__ __forceinline__ void bwd_dst_node_fast(const GatArgs& a, int64_t v, int beg, int deg, int lane) {
+    const Nbr4<H> n = softmax4<H, false>(a, v, beg, deg, lane, nullptr);   // recomputed: same values as forward
+    const float inv_h = 1.f / (float)H;
+    float d[H][4];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[h][j] = 0.f;
+    for (int col = lane * 4; col < a.F; col += 128) {
+        float4 idsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 gom;
+        if (a.mean_heads) gom = scale4(inv_h, ldg4(a.g_out + v * a.ldg + col));
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const int hc = h * a.F + col;
+            float4 z[4];
+            float4 go, y;
+            if (a.mean_heads) {
+                y = act4(add_res_bias(a, gather_rows<H>(n, h, hc, z), v, hc), a.act);
+                go = gom;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) z[j] = ldg4(n.row[j] + hc);
+                go = ldg4(a.g_out + v * a.ldg + hc);
+                y = ldg4(a.out_saved + v * a.ldo + hc);
+            }
+            const float4 gq = mul4(go, actgrad4(y, a.act));
+            st4(a.G + v * a.ldG + hc, gq);
+            if (a.res_mode == 2) {
+                if (a.xres_cols == a.F) idsum = add4(idsum, gq);
+                else st4(a.dxres + v * a.ldxres + hc, gq);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[h][j] += dot4(gq, z[j]);
+        }
+        if (a.res_mode == 2 && a.xres_cols == a.F) st4(a.dxres + v * a.ldxres + col, idsum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[h][j] += __shfl_xor_sync(kFull, d[h][j], o);
+    // softmax + LeakyReLU backward, redundantly on every lane (<= 4 edges x H heads)
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float er = __ldg(a.Y + v * a.ldy + a.er_off + h);
+        float da[4], wsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // d(a_drop)/d(a) = keep/(1-p) = w/att (0 when dropped or beyond the degree)
+            const float ks = n.att[h][j] > 0.f ? n.w[h][j] / n.att[h][j] : 0.f;
+            da[j] = j < deg ? d[h][j] * ks : 0.f;
+            wsum += n.att[h][j] * da[j];
+        }
+        float der = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < deg) {
+                const float raw = __ldg(n.row[j] + a.el_off + h) + er;
+                const float dsv = n.att[h][j] * (da[j] - wsum) * (raw > 0.f ? 1.f : a.neg_slope);
+                if (lane == j) a.ds[(int64_t)(beg + j) * H + h] = dsv;
+                der += dsv;
+            }
+        }
+        if (lane == 0) a.dY[v * a.ldy + a.er_off + h] = der;
+    }
+}
+
+// backward, source side: dz[u,h,:] = sum over out-edges (u->v) of a_drop * g[v,h,:];  del[u,h] = sum of ds
+template <int H>
+__device__ __forceinline__ void bwd_src_node_fast(const GatArgs& a, int64_t u, int beg, int deg, int lane) {
+    const int j = lane & 3, h = min((lane >> 2) & 1, H - 1);
+    const int qidx = beg + min(j, deg - 1);
+    const int s = __ldg(a.out_slot + qidx);
+    const int v = __ldg(a.out_dst + qidx);
+    const bool valid = j < deg;
+    const float w = valid ? __ldg(a.att_in + (int64_t)s * H + h) * keep_scale(a, s, h) : 0.f;
+    float dsv = valid ? __ldg(a.ds + (int64_t)s * H + h) : 0.f;
+    dsv += __shfl_xor_sync(kFull, dsv, 1);
+    dsv += __shfl_xor_sync(kFull, dsv, 2);
+    if (j == 0 && lane < 4 * H) a.dY[u * a.ldy + a.el_off + h] = dsv;
+    const float* grow[4];
+    float wj[H][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        grow[jj] = a.G + (int64_t)__shfl_sync(kFull, v, jj) * a.ldG;
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) wj[hh][jj] = __shfl_sync(kFull, w, jj + 4 * hh);
+    }
+    float* drow = a.dY + u * a.ldy;
+    for (int col = lane * 4; col < a.F; col += 128) {
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) {
+            const int hc = hh * a.F + col;
+            float4 gv[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) gv[jj] = ldg4(grow[jj] + hc);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc = fma4(wj[hh][jj], gv[jj], acc);
+            st4(drow + hc, acc);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kAggThreads) gat_agg_fwd_kernel(const GatArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -92,8 +315,26 @@ __global__ void __launch_bounds__(kAggThreads) gat_agg_fwd_kernel(const GatArgs 
     const float inv_h = 1.f / (float)a.H;
     for (int64_t v = warp0; v < a.N; v += nwarps) {
         const int beg = __ldg(a.in_ptr + v), end = __ldg(a.in_ptr + v + 1);
+        const int deg = end - beg;
+        if (a.skip_fast && deg >= 1 && deg <= 4) continue;
         for (int h = 0; h < a.H; ++h) edge_softmax_warp(a, v, h, beg, end, lane);
         __syncwarp();
+        if (false) {
+            // airway trees: in-degree <= 4 (3 neighbours + self loop)
+            const Edge4 e0 = load_edges4(a, a.att, beg, deg, 0);
+            const Edge4 e1 = a.H > 1 ? load_edges4(a, a.att, beg, deg, 1) : e0;
+            for (int col = lane * 4; col < a.F; col += 128) {
+                float4 y0 = act4(add_res_bias(a, gather4(a, e0, deg, col), v, col), a.act);
+                if (a.H > 1) {
+                    float4 y1 = act4(add_res_bias(a, gather4(a, e1, deg, a.F + col), v, a.F + col), a.act);
+                    if (a.mean_heads) st4(a.out + v * a.ldo + col, scale4(inv_h, add4(y0, y1)));
+                    else { st4(a.out + v * a.ldo + col, y0); st4(a.out + v * a.ldo + a.F + col, y1); }
+                } else {
+                    st4(a.out + v * a.ldo + col, y0);      // one head: its mean is itself
+                }
+            }
+            continue;
+        }
         for (int col = lane * 4; col < a.F; col += 128) {
             float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int h = 0; h < a.H; ++h) {
@@ -110,28 +351,35 @@ __global__ void __launch_bounds__(kAggThreads) gat_agg_fwd_kernel(const GatArgs 
 //   g[v,h,:]  = g_out * act'(y)                      -> G (== the dres columns of dY when the residual is linear)
 //   dot_j     = <g[v,h,:], z[u_j,h,:]>                -> d(a_drop_j)
 //   ds_j      = a_j (da_j - sum_k a_k da_k) * leaky'(el[u_j]+er[v])   -> ds[slot*H+h];   der[v,h] = sum_j ds_j
+template <int NCH>
 __global__ void __launch_bounds__(kAggThreads) gat_agg_bwd_dst_kernel(const GatArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float inv_h = 1.f / (float)a.H;
-    const int nch = (a.F + 127) / 128;
     for (int64_t v = warp0; v < a.N; v += nwarps) {
         const int beg = __ldg(a.in_ptr + v), end = __ldg(a.in_ptr + v + 1);
-        float4 idsum[kMaxCh];   // identity-residual gradient (summed over heads when xres_cols == F)
+        const int deg = end - beg;
+        if (a.skip_fast && deg >= 1 && deg <= 4) continue;
+        const bool fast = false;
+        float4 idsum[NCH];   // identity-residual gradient (summed over heads when xres_cols == F)
 #pragma unroll
-        for (int c = 0; c < kMaxCh; ++c) idsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < NCH; ++c) idsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int h = 0; h < a.H; ++h) {
-            float4 gq[kMaxCh];
+            Edge4 e;
+            if (fast) e = load_edges4(a, a.att_in, beg, deg, h);
+            float4 gq[NCH];
 #pragma unroll
-            for (int c = 0; c < kMaxCh; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 gq[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int col = (c * 32 + lane) * 4;
-                if (c < nch && col < a.F) {
+                if (col < a.F) {
                     float4 go, y;
                     if (a.mean_heads) {
                         go = scale4(inv_h, ldg4(a.g_out + v * a.ldg + col));
-                        y = act4(pre_chunk(a, a.att_in, v, h, col, beg, end), a.act);
+                        const float4 pre = fast ? add_res_bias(a, gather4(a, e, deg, h * a.F + col), v, h * a.F + col)
+                                                : pre_chunk(a, a.att_in, v, h, col, beg, end);
+                        y = act4(pre, a.act);
                     } else {
                         go = ldg4(a.g_out + v * a.ldg + h * a.F + col);
                         y = ldg4(a.out_saved + v * a.ldo + h * a.F + col);
@@ -144,42 +392,84 @@ __global__ void __launch_bounds__(kAggThreads) gat_agg_bwd_dst_kernel(const GatA
                     }
                 }
             }
-            // d(a_drop_j) for every in-edge, staged in ds[] so any degree works
-            for (int s = beg; s < end; ++s) {
-                const int u = __ldg(a.in_src + s);
-                float d = 0.f;
-#pragma unroll
-                for (int c = 0; c < kMaxCh; ++c) {
-                    const int col = (c * 32 + lane) * 4;
-                    if (c < nch && col < a.F) d += dot4(gq[c], ldg4(a.Y + (int64_t)u * a.ldy + h * a.F + col));
-                }
-                d = warp_sum(d);
-                if (lane == 0) a.ds[(int64_t)s * a.H + h] = d * keep_scale(a, s, h);
-            }
-            __syncwarp();
-            float wsum = 0.f;
-            for (int s = beg + lane; s < end; s += 32)
-                wsum += __ldg(a.att_in + (int64_t)s * a.H + h) * a.ds[(int64_t)s * a.H + h];
-            wsum = warp_sum(wsum);
             const float er = __ldg(a.Y + v * a.ldy + a.er_off + h);
-            float der = 0.f;
-            for (int s = beg + lane; s < end; s += 32) {
-                const int u = __ldg(a.in_src + s);
-                const float raw = __ldg(a.Y + (int64_t)u * a.ldy + a.el_off + h) + er;
-                const float de = __ldg(a.att_in + (int64_t)s * a.H + h) * (a.ds[(int64_t)s * a.H + h] - wsum);
-                const float dsv = de * (raw > 0.f ? 1.f : a.neg_slope);
-                a.ds[(int64_t)s * a.H + h] = dsv;
-                der += dsv;
+            if (fast) {
+                // d(a_drop_j) = <g, z[u_j]> for the (<= 4) in-edges: row loads issued together, reductions interleaved
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int col = (c * 32 + lane) * 4;
+                    if (col < a.F) {
+                        float4 z[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            z[j] = j < deg ? ldg4(a.Y + (int64_t)e.u[j] * a.ldy + h * a.F + col)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) d[j] += dot4(gq[c], z[j]);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[j] += __shfl_xor_sync(kFull, d[j], o);
+                }
+                // softmax backward, every lane redundantly (4 edges)
+                float att_j[4], da[4], wsum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    att_j[j] = j < deg ? __ldg(a.att_in + (int64_t)(beg + j) * a.H + h) : 0.f;
+                    da[j] = j < deg ? d[j] * keep_scale(a, beg + j, h) : 0.f;
+                    wsum += att_j[j] * da[j];
+                }
+                float der = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < deg) {
+                        const float raw = __ldg(a.Y + (int64_t)e.u[j] * a.ldy + a.el_off + h) + er;
+                        const float dsv = att_j[j] * (da[j] - wsum) * (raw > 0.f ? 1.f : a.neg_slope);
+                        if (lane == j) a.ds[(int64_t)(beg + j) * a.H + h] = dsv;
+                        der += dsv;
+                    }
+                }
+                if (lane == 0) a.dY[v * a.ldy + a.er_off + h] = der;
+            } else {
+                // general degree: d(a_drop_j) staged in ds[]
+                for (int s = beg; s < end; ++s) {
+                    const int u = __ldg(a.in_src + s);
+                    float d = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int col = (c * 32 + lane) * 4;
+                        if (col < a.F) d += dot4(gq[c], ldg4(a.Y + (int64_t)u * a.ldy + h * a.F + col));
+                    }
+                    d = warp_sum(d);
+                    if (lane == 0) a.ds[(int64_t)s * a.H + h] = d * keep_scale(a, s, h);
+                }
+                __syncwarp();
+                float wsum = 0.f;
+                for (int s = beg + lane; s < end; s += 32)
+                    wsum += __ldg(a.att_in + (int64_t)s * a.H + h) * a.ds[(int64_t)s * a.H + h];
+                wsum = warp_sum(wsum);
+                float der = 0.f;
+                for (int s = beg + lane; s < end; s += 32) {
+                    const int u = __ldg(a.in_src + s);
+                    const float raw = __ldg(a.Y + (int64_t)u * a.ldy + a.el_off + h) + er;
+                    const float de = __ldg(a.att_in + (int64_t)s * a.H + h) * (a.ds[(int64_t)s * a.H + h] - wsum);
+                    const float dsv = de * (raw > 0.f ? 1.f : a.neg_slope);
+                    a.ds[(int64_t)s * a.H + h] = dsv;
+                    der += dsv;
+                }
+                der = warp_sum(der);
+                if (lane == 0) a.dY[v * a.ldy + a.er_off + h] = der;
+                __syncwarp();
             }
-            der = warp_sum(der);
-            if (lane == 0) a.dY[v * a.ldy + a.er_off + h] = der;
-            __syncwarp();
         }
         if (a.res_mode == 2 && a.xres_cols == a.F) {
 #pragma unroll
-            for (int c = 0; c < kMaxCh; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 const int col = (c * 32 + lane) * 4;
-                if (c < nch && col < a.F) st4(a.dxres + v * a.ldxres + col, idsum[c]);
+                if (col < a.F) st4(a.dxres + v * a.ldxres + col, idsum[c]);
             }
         }
     }
@@ -193,6 +483,7 @@ __global__ void __launch_bounds__(kAggThreads) gat_agg_bwd_src_kernel(const GatA
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t u = warp0; u < a.N; u += nwarps) {
         const int beg = __ldg(a.out_ptr + u), end = __ldg(a.out_ptr + u + 1);
+        if (a.skip_fast && end - beg >= 1 && end - beg <= 4) continue;
         for (int h = 0; h < a.H; ++h) {
             float del = 0.f;
             for (int q = beg + lane; q < end; q += 32) del += __ldg(a.ds + (int64_t)__ldg(a.out_slot + q) * a.H + h);
@@ -210,6 +501,30 @@ __global__ void __launch_bounds__(kAggThreads) gat_agg_bwd_src_kernel(const GatA
             }
         }
     }
+}
+
+// which = 0 forward, 1 backward-destination, 2 backward-source
+template <int H, int WHICH>
+__global__ void __launch_bounds__(kAggThreads) gat_fast_kernel(const GatArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int32_t* ptr = WHICH == 2 ? a.out_ptr : a.in_ptr;
+    for (int64_t v = warp0; v < a.N; v += nwarps) {
+        const int beg = __ldg(ptr + v), deg = __ldg(ptr + v + 1) - beg;
+        if (deg < 1 || deg > 4) continue;            // left to the general kernel
+        if (WHICH == 0) fwd_node_fast<H>(a, v, beg, deg, lane);
+        else if (WHICH == 1) bwd_dst_node_fast<H>(a, v, beg, deg, lane);
+        else bwd_src_node_fast<H>(a, v, beg, deg, lane);
+    }
+}
+
+template <int WHICH>
+static int launch_fast(const GatArgs& a, cudaStream_t st, unsigned grid) {
+    if (a.H == 1) gat_fast_kernel<1, WHICH><<<grid, kAggThreads, 0, st>>>(a);
+    else gat_fast_kernel<2, WHICH><<<grid, kAggThreads, 0, st>>>(a);
+    SPGNN_LAUNCH_OK();
+    return SPGNN_OK;
 }
 
 static inline unsigned agg_grid(int64_t N) {
@@ -256,7 +571,12 @@ extern "C" int spgnn_gat_agg_fwd(const float* Y, int64_t ldy, int64_t res_off, i
     a.bias = bias; a.act = act; a.neg_slope = negative_slope; a.mean_heads = mean_heads;
     a.drop_p = attn_drop_p; a.seed = seed; a.in_ptr = in_ptr; a.in_src = in_src;
     a.N = N; a.H = (int)H; a.F = (int)F; a.out = out; a.ldo = ldo; a.att = att;
-    gat_agg_fwd_kernel<<<agg_grid(N), kAggThreads, 0, as_stream(stream)>>>(a);
+    a.skip_fast = H <= 2;
+    if (a.skip_fast) {
+        rc = launch_fast<0>(a, as_stream(stream), agg_grid(N));
+        if (rc) return rc;
+    }
+    gat_agg_fwd_kernel<<<agg_grid(N), kAggThreads, 0, as_stream(stream)>>>(a);   // nodes with other degrees (none in a tree)
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }
@@ -291,8 +611,20 @@ extern "C" int spgnn_gat_agg_bwd(const float* g_out, int64_t ldg, const float* o
     a.dY = dY; a.dxres = dxres; a.ds = ds_ws;
     if (res_mode == 1) { a.G = dY + res_off; a.ldG = ldy; } else { a.G = g_ws; a.ldG = H * F; }
     cudaStream_t st = as_stream(stream);
-    gat_agg_bwd_dst_kernel<<<agg_grid(N), kAggThreads, 0, st>>>(a);
+    a.skip_fast = H <= 2;
+    if (a.skip_fast) {
+        rc = launch_fast<1>(a, st, agg_grid(N));
+        if (rc) return rc;
+    }
+    if (F <= 128) gat_agg_bwd_dst_kernel<1><<<agg_grid(N), kAggThreads, 0, st>>>(a);
+    else if (F <= 256) gat_agg_bwd_dst_kernel<2><<<agg_grid(N), kAggThreads, 0, st>>>(a);
+    else if (F <= 512) gat_agg_bwd_dst_kernel<4><<<agg_grid(N), kAggThreads, 0, st>>>(a);
+    else gat_agg_bwd_dst_kernel<8><<<agg_grid(N), kAggThreads, 0, st>>>(a);
     SPGNN_LAUNCH_OK();
+    if (a.skip_fast) {
+        rc = launch_fast<2>(a, st, agg_grid(N));
+        if (rc) return rc;
+    }
     gat_agg_bwd_src_kernel<<<agg_grid(N), kAggThreads, 0, st>>>(a);
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;

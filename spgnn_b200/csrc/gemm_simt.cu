@@ -322,6 +322,13 @@ int simt_linear_bwd_weight(const float* dC, int64_t lddc, const float* A, int64_
     return SPGNN_OK;
 }
 
+void reduce_splits(const float* ws, int64_t splits, int64_t N, int64_t K, float* out, int64_t ldo, cudaStream_t st) {
+    const int64_t total = N * K;
+    const int64_t want = ceil_div(total, 256), cap = (int64_t)sm_count() * 8;
+    reduce_splits_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ws, splits, N * K, N, K, out, ldo);
+    count_launch();
+}
+
 }  // namespace spgnn
 
 using namespace spgnn;

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import nn as snn
+from . import nn as snn, ops
 from ._lib import SpgnnError
 
 
@@ -29,9 +29,19 @@ def set_trainable(model, trainable):
 
 
 def _feats(g, h, key="fvs"):
+    """Layer-0 input: fp32 with 16-byte aligned rows (what the tensor-core projection's 128-bit loads need); a
+    tensor with an odd row stride (e.g. a contiguous [N,39] pos_enc) is re-laid out once and cached on the graph."""
     x = g.ndata[key] if h is None else h
     if x.dtype != torch.float32:
         x = x.float()
+    if x.dim() == 2 and (x.stride(1) != 1 or x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0):
+        cache = g.__dict__.setdefault("_aligned_feats", {})
+        hit = cache.get(key)
+        if hit is None or hit[0] is not x:
+            y = ops.empty_padded(x.shape[0], x.shape[1], x.device)
+            y.copy_(x)
+            cache[key] = hit = (x, y)
+        x = hit[1]
     return x
 
 

@@ -13,7 +13,7 @@ from ._lib import SpgnnError, lib, ptr, require_cuda, stream
 ACT = {None: 0, "none": 0, "elu": 1, "tanh": 2, "relu": 3, "leaky_relu": 4}
 
 # projection arithmetic: 0 = fp32 SIMT, 1 = tcgen05 split-bf16 tensor cores (see csrc/gemm_tc.cu)
-GEMM_MODE = 0
+GEMM_MODE = 1
 
 _seed_state = {"seed": 0x5350474E, "counter": 0}
 
@@ -55,6 +55,10 @@ def empty_padded(rows, cols, device):
     return torch.empty(rows, _pad4(cols), dtype=torch.float32, device=device)[:, :cols]
 
 
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
 def colsum(x):
     x = _rows(x)
     M, N = x.shape
@@ -80,8 +84,10 @@ class LinearFn(Function):
             raise SpgnnError(f"linear: weight has {W.shape[1]} columns, input has {K1}+{K2}")
         y = empty_padded(M, N, x1.device)
         b = bias.contiguous() if bias is not None else None
+        ws = _ws(lib().linear_fwd_ws(N, K1, K2), x1.device) if GEMM_MODE == 1 else None
         lib().linear_fwd(ptr(x1), x1.stride(0), K1, ptr(x2), x2.stride(0) if x2 is not None else 0, K2,
-                         ptr(W), W.stride(0), ptr(b), act, float(slope), ptr(y), y.stride(0), M, N, GEMM_MODE, stream(),
+                         ptr(W), W.stride(0), ptr(b), act, float(slope), ptr(y), y.stride(0), M, N, GEMM_MODE,
+                         ptr(ws), ws.numel() if ws is not None else 0, stream(),
                          _key=("flops", 2.0 * M * N * (K1 + K2)))
         ctx.save_for_backward(x1, x2, W, y if act else None)
         ctx.cfg = (act, float(slope), bias is not None)
@@ -103,12 +109,16 @@ class LinearFn(Function):
         dx1 = dx2 = dW = db = None
         if ctx.needs_input_grad[0]:
             dx1 = empty_padded(M, K1, g.device)
+            ws = _ws(L.linear_bwd_input_ws(N, K1), g.device) if GEMM_MODE == 1 else None
             L.linear_bwd_input(ptr(g), g.stride(0), ptr(W), W.stride(0), 0, ptr(dx1), dx1.stride(0), M, N, K1,
-                               GEMM_MODE, stream(), _key=("flops", 2.0 * M * N * K1))
+                               GEMM_MODE, ptr(ws), ws.numel() if ws is not None else 0, stream(),
+                               _key=("flops", 2.0 * M * N * K1))
         if x2 is not None and ctx.needs_input_grad[1]:
             dx2 = empty_padded(M, K2, g.device)
+            ws = _ws(L.linear_bwd_input_ws(N, K2), g.device) if GEMM_MODE == 1 else None
             L.linear_bwd_input(ptr(g), g.stride(0), ptr(W), W.stride(0), K1, ptr(dx2), dx2.stride(0), M, N, K2,
-                               GEMM_MODE, stream(), _key=("flops", 2.0 * M * N * K2))
+                               GEMM_MODE, ptr(ws), ws.numel() if ws is not None else 0, stream(),
+                               _key=("flops", 2.0 * M * N * K2))
         if ctx.needs_input_grad[2]:
             dW = empty_padded(N, K1 + K2, g.device)
             for x, koff, K in ((x1, 0, K1), (x2, K1, K2)):

@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from ._lib import SpgnnError, lib, ptr, stream
+from .ops import empty_padded
 
 
 def select_anchors(g, fvs_out=None, pos_enc_dim=39):
@@ -31,7 +32,7 @@ def distance_pos_enc(g, anchors=None, pos_enc_dim=39, store=True):
         anchors = select_anchors(g, pos_enc_dim=pos_enc_dim)
     anchors = anchors.to(torch.int32).contiguous()
     pos_enc_dim = anchors.shape[1]
-    pe = torch.empty(g.num_nodes, pos_enc_dim, dtype=torch.float32, device=g.device)
+    pe = empty_padded(g.num_nodes, pos_enc_dim, g.device)      # 16-byte rows: the projection reads it with 128-bit loads
     diam = torch.empty(g.batch_size, dtype=torch.int32, device=g.device)
     flags = torch.empty(1, dtype=torch.int32, device=g.device)
     nbytes = int(lib().pe_dist_ws_bytes(g.batch_size, g.max_nodes))
@@ -49,7 +50,7 @@ def distance_pos_enc(g, anchors=None, pos_enc_dim=39, store=True):
 
 def rw_pos_enc(g, pos_enc_dim=39, store=True):
     """diag((A D^-1)^k), k = 1..pos_enc_dim on the self-loop-free graph, fp32 [N, pos_enc_dim]."""
-    pe = torch.empty(g.num_nodes, pos_enc_dim, dtype=torch.float32, device=g.device)
+    pe = empty_padded(g.num_nodes, pos_enc_dim, g.device)
     lib().pe_rw_init(ptr(g.node_off), ptr(g.in_ptr), ptr(g.in_src), g.batch_size, pos_enc_dim, g.max_nodes, ptr(pe),
                      pe.stride(0), stream())
     if store:

@@ -102,9 +102,15 @@ def test_graph_errors(mods):
 
 
 # ------------------------------------------------------------------------------------------------ projection
-@pytest.mark.parametrize("M,K1,K2,N", [(300, 64, 0, 48), (1000, 1024, 39, 130), (257, 39, 0, 258), (513, 100, 7, 22)])
-def test_linear_fwd_bwd_against_fp64(mods, M, K1, K2, N):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("M,K1,K2,N", [(300, 64, 0, 48), (1000, 1024, 39, 130), (257, 39, 0, 258), (513, 100, 7, 22),
+                                       (128, 64, 0, 16), (5000, 1024, 40, 1028), (4096, 192, 0, 4100)])
+def test_linear_fwd_bwd_against_fp64(mods, M, K1, K2, N, mode, monkeypatch):
+    """mode 0: fp32 SIMT kernels; mode 1: tcgen05 split-bf16 tensor-core kernels (falls back per call when an
+    operand is not 16-byte aligned).  Both against an fp64 reference."""
     ops = mods["ops"]
+    monkeypatch.setattr(ops, "GEMM_MODE", mode)
+    tol = 1e-5 if mode == 0 else 4e-5
     gen = torch.Generator().manual_seed(M + N)
     x1 = torch.randn(M, K1, generator=gen)
     x2 = torch.randn(M, K2, generator=gen) if K2 else None
@@ -119,9 +125,9 @@ def test_linear_fwd_bwd_against_fp64(mods, M, K1, K2, N):
     Wd, bd = W.double().requires_grad_(), b.double().requires_grad_()
     yd = torch.nn.functional.elu(torch.cat(xd, 1) @ Wd.t() + bd)
     yd.backward(go.double())
-    assert rel_err(y.detach().cpu(), yd.detach()) < 1e-5
+    assert rel_err(y.detach().cpu(), yd.detach()) < tol
     for a, r in zip(xs + [Wc, bc], xd + [Wd, bd]):
-        assert rel_err(a.grad.cpu(), r.grad) < 1e-5
+        assert rel_err(a.grad.cpu(), r.grad) < tol
 
 
 # ------------------------------------------------------------------------------------------------ models
@@ -157,10 +163,27 @@ def _margin_aware_flips(a, b, tol):
     return int((margin[flips] > tol).sum())
 
 
-@pytest.mark.parametrize("name", sorted(FULL_MODELS))
-def test_full_width_forward_backward_vs_oracle(mods, name):
-    """exp_settings widths, 6 ragged trees, eval-mode forward + all parameter gradients vs the CPU oracle."""
+def _full_cases():
+    out = []
+    for name in sorted(FULL_MODELS):
+        out.append((name, 1))                       # tensor-core projections (the default)
+        if FULL_MODELS[name][0] in ("gin", "sage", "gcn"):
+            out.append((name, 0))                   # fp32 SIMT projections
+    return out
+
+
+@pytest.mark.parametrize("name,mode", _full_cases())
+def test_full_width_forward_backward_vs_oracle(mods, name, mode, monkeypatch):
+    """exp_settings widths, 6 ragged trees, eval-mode forward + all parameter gradients vs the CPU oracle.
+
+    GAT-family models are checked end to end with the tensor-core projections.  SAGE's max-pool and GIN's / SAGE's
+    ReLU-type kinks make the GRADIENT a discontinuous function of the forward values: a 1e-6 perturbation of two
+    nearly tied neighbours re-routes one sample's gradient (a ~1/sqrt(N) change of that weight row).  For those the
+    strict gradient bar is applied with the fp32 SIMT projections (mode 0), and with tensor cores (mode 1) the
+    forward outputs keep the strict bar while gradients get a 3e-2 bar."""
     kind, cfg = FULL_MODELS[name]
+    monkeypatch.setattr(mods["ops"], "GEMM_MODE", mode)
+    grad_tol = GRAD_TOL if (mode == 0 or kind in ("gat", "spgnn")) else 3e-2
     scans = _scan_dicts(mods, 1000, 6, ragged=True)
     pos = None
     if kind == "spgnn":
@@ -211,7 +234,7 @@ def test_full_width_forward_backward_vs_oracle(mods, name):
             continue
         assert p.grad is not None, k
         abs_err = float((p.grad.cpu().double() - r.double()).abs().max())
-        assert abs_err <= GRAD_TOL * float(r.abs().max()) or abs_err <= 1e-6 * gmax, \
+        assert abs_err <= grad_tol * float(r.abs().max()) or abs_err <= 1e-6 * gmax, \
             (name, k, rel_err(p.grad.cpu(), r), abs_err, gmax)
 
 
