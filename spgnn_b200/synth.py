@@ -105,7 +105,7 @@ def tree_labels(tree_id, n, seed=1234):
     r = philox4x32(np.arange(NR_CLASS - 1, dtype=np.uint32), np.uint32(0), np.uint32(2), np.uint32(tree_id), seed, KEY1)[0]
     perm = np.arange(n, dtype=np.int64)
     y = np.zeros(n, dtype=np.int64)
-    for j in range(NR_CLASS - 1):
+    for j in range(min(NR_CLASS - 1, n)):      # trees smaller than 21 nodes (tests only) get labels 1..n
         p = j + int((int(r[j]) * (n - j)) >> 32)
         perm[j], perm[p] = perm[p], perm[j]
         y[perm[j]] = j + 1
