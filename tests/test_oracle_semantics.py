@@ -79,10 +79,14 @@ def test_gcn_known_answer_star():
 
 def test_gatconv_gradcheck_fp64():
     torch.manual_seed(2)
-    g, _, x = _tree_graph(k=4, fdim=5)
-    conv = dgl_ops.GATConv(5, 3, 2, residual=True, activation=torch.tanh).double()
-    x = x.clone().requires_grad_()
-    assert torch.autograd.gradcheck(lambda t: conv(g, t), (x,), eps=1e-6, atol=1e-5)
+    g, _, _ = _tree_graph(k=4, fdim=5)
+    for act in (None, torch.tanh, F.elu):
+        for res in (False, True):
+            conv = dgl_ops.GATConv(5, 3, 2, residual=res, activation=act).double()
+            x = torch.randn(g.num_nodes, 5, dtype=torch.float64, requires_grad=True)
+            assert torch.autograd.gradcheck(lambda t: conv(g, t), (x,), eps=1e-6, atol=1e-5)
+    e = torch.randn(g.number_of_edges(), 2, 1, dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda t: dgl_ops.edge_softmax(g, t), (e,), eps=1e-6, atol=1e-5)
 
 
 def test_batch_equals_separate_graphs_and_permutation_equivariance():
