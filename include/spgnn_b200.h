@@ -112,6 +112,12 @@ int64_t spgnn_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K);
 int spgnn_linear_bwd_weight(const float* dC, int64_t lddc, const float* A, int64_t lda,
                             float* dW, int64_t lddw, int64_t k_off, int64_t M, int64_t N, int64_t K,
                             void* ws, int mode, void* stream);
+/* Two-source form: dW[N, K1+K2] (lddw) = dC[M,N]^T * [A1 | A2] in ONE pass over dC (mode 1: 256 x BN tensor-core tiles
+ * with two TMEM accumulators sharing the dC tile). */
+int64_t spgnn_linear_bwd_weight2_ws(int64_t M, int64_t N, int64_t K1, int64_t K2);
+int spgnn_linear_bwd_weight2(const float* dC, int64_t lddc, const float* A1, int64_t lda1, int64_t K1,
+                             const float* A2, int64_t lda2, int64_t K2, float* dW, int64_t lddw,
+                             int64_t M, int64_t N, void* ws, int mode, void* stream);
 /* out[n] = sum_m X[m, n]  (bias gradients).  ws: spgnn_colsum_ws(N) bytes. */
 int64_t spgnn_colsum_ws(int64_t N);
 int spgnn_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* ws, void* stream);

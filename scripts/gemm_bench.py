@@ -31,12 +31,14 @@ for name, K1, K2, N in LAYERS:
     for mode in modes:
         ws1 = torch.empty(int(L.linear_fwd_ws(N, K1, K2)) + 16, dtype=torch.uint8, device="cuda")
         ws2 = torch.empty(int(L.linear_bwd_input_ws(N, K1)) + 16, dtype=torch.uint8, device="cuda")
-        ws3 = torch.empty(int(L.linear_bwd_weight_ws(M, N, K1)) + 16, dtype=torch.uint8, device="cuda")
+        ws3 = torch.empty(int(L.linear_bwd_weight2_ws(M, N, K1, K2)) + 16, dtype=torch.uint8, device="cuda")
         f = lambda: L.linear_fwd(ptr(x1), x1.stride(0), K1, ptr(x2), x2.stride(0) if K2 else 0, K2, ptr(W), W.stride(0), None, 0, 0.0,
                                  ptr(y), y.stride(0), M, N, mode, ptr(ws1), ws1.numel(), stream())
         b = lambda: L.linear_bwd_input(ptr(g), g.stride(0), ptr(W), W.stride(0), 0, ptr(dx), dx.stride(0), M, N, K1, mode, ptr(ws2), ws2.numel(), stream())
-        w = lambda: L.linear_bwd_weight(ptr(g), g.stride(0), ptr(x1), x1.stride(0), ptr(dW), dW.stride(0), 0, M, N, K1, ptr(ws3), mode, stream())
+        w = lambda: L.linear_bwd_weight2(ptr(g), g.stride(0), ptr(x1), x1.stride(0), K1, ptr(x2), x2.stride(0) if K2 else 0, K2, ptr(dW), dW.stride(0), M, N, ptr(ws3), mode, stream())
+        w1 = lambda: L.linear_bwd_weight(ptr(g), g.stride(0), ptr(x1), x1.stride(0), ptr(dW), dW.stride(0), 0, M, N, K1, ptr(ws3), mode, stream())
         tf, tb, tw = timeit(f), timeit(b), timeit(w)
+        tw1 = timeit(w1)
         fl = 2.0 * M * N
-        print(f"{name:8s} mode {mode} K={K1}+{K2} N={N}: fwd {tf:7.2f} ms {fl*K/tf/1e9:7.1f} TF | dX {tb:7.2f} ms {fl*K1/tb/1e9:7.1f} TF | dW {tw:7.2f} ms {fl*K1/tw/1e9:7.1f} TF", flush=True)
+        print(f"{name:8s} mode {mode} K={K1}+{K2} N={N}: fwd {tf:7.2f} ms {fl*K/tf/1e9:7.1f} TF | dX {tb:7.2f} ms {fl*K1/tb/1e9:7.1f} TF | dW {tw:7.2f} ms {fl*K/tw/1e9:7.1f} TF | dW(v1,src1) {tw1:7.2f} ms", flush=True)
     del x1, x2, y, dx, g

@@ -546,6 +546,211 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tn_kernel(const TnArgs g) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- TN kernel v2 (dW)
+// D[k, n] = sum over nodes m of X[m, k] * dY[m, n]  (= dW^T): a CTA owns 256 k-columns of X (two M=128 accumulators
+// that SHARE the dY tile) x BN <= 256 dY-columns, so each fp32 operand element fetched from L2 feeds twice the
+// math of a 128x128 tile (the v1 kernel was L2-bandwidth bound).  X may come from two sources ([X1 | X2], the
+// un-materialised torch.cat).  BK = 32 nodes per stage, 3 stages, MN-major SW128 tiles, rolling register prefetch.
+// TMEM lane = k, so the epilogue's per-column stores are 32 consecutive floats of a dW row: coalesced as is.
+struct Tn2Args {
+    const float* X1; int64_t ldx1; int K1;
+    const float* X2; int64_t ldx2; int K2;
+    const float* dY; int64_t lddy; int N;
+    float* out; int64_t ldo; int64_t split_stride;      // partial sums [split][N][K1+K2]
+    int64_t M; int64_t rows_per_split;
+    int nk1, nk2, nt_n, BN;                             // 256-wide k tiles of source 1 / 2, n tiles, n tile width
+};
+constexpr int T2_BK = 32;
+constexpr int T2_ABYTES = 4 * 4096;            // 256 mn x 32 rows x bf16 = 4 MN-blocks of 4 KB (one plane)
+constexpr int T2_BBYTES = 4 * 4096;            // up to 256 mn
+constexpr int T2_STAGE = 2 * T2_ABYTES + 2 * T2_BBYTES;   // 64 KB
+constexpr int T2_STAGES = 3;
+constexpr int T2_SMEM = T2_STAGES * T2_STAGE + 1024 + 256;
+
+struct SharedTn2 {
+    uint64_t full[T2_STAGES];
+    uint64_t empty[T2_STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) tc_tn2_kernel(const Tn2Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    SharedTn2* sh = reinterpret_cast<SharedTn2*>(smem + T2_STAGES * T2_STAGE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    constexpr int kProdThreads = 32 * kProdWarps;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) {
+            mbar_init(smem_u32(&sh->full[s]), kProdThreads);
+            mbar_init(smem_u32(&sh->empty[s]), 1);
+        }
+        mbar_init(smem_u32(&sh->tmem_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == kEpiWarps) tmem_alloc(smem_u32(&sh->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    // work item: blockIdx.x = k-tile * nt_n + n-tile, blockIdx.y = split over the nodes
+    const int tk = blockIdx.x / g.nt_n, tn = blockIdx.x % g.nt_n;
+    const bool s2 = tk >= g.nk1;
+    const float* X = s2 ? g.X2 : g.X1;
+    const int64_t ldx = s2 ? g.ldx2 : g.ldx1;
+    const int Kv = s2 ? g.K2 : g.K1;                         // valid columns of this source
+    const int kbase = (s2 ? tk - g.nk1 : tk) * 256;          // first column within the source
+    const int kout = (s2 ? g.K1 : 0) + kbase;                // first column in dW
+    const int n0 = tn * g.BN;
+    const int ncols = min(g.BN, g.N - n0);
+    const int n_mma = (ncols + 15) & ~15;
+    const int64_t mbeg = (int64_t)blockIdx.y * g.rows_per_split;
+    const int64_t mend = min(g.M, mbeg + g.rows_per_split);
+    const int nkb = (int)((mend - mbeg + T2_BK - 1) / T2_BK);
+    const bool two_acc = kbase + 128 < Kv;                   // second accumulator has any valid column
+
+    if (warp < kEpiWarps) {
+        mbar_wait(smem_u32(&sh->tmem_full), 0);
+        tc_fence_after();
+        float* obase = g.out + (int64_t)blockIdx.y * g.split_stride;
+        for (int acc = 0; acc < (two_acc ? 2 : 1); ++acc) {
+            const int kk = kbase + acc * 128 + warp * 32 + lane;        // column within the source
+            const bool kok = kk < Kv;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
+            float* ocol = obase + (kout + acc * 128 + warp * 32 + lane);
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (kok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < ncols) ocol[(int64_t)(n0 + c0 + j) * g.ldo] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    } else if (warp == kEpiWarps) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(n_mma, true);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % T2_STAGES;
+                const uint32_t sp = (kb / T2_STAGES) & 1;
+                mbar_wait(smem_u32(&sh->full[s]), sp);
+                tc_fence_after();
+                const uint32_t a_hi = smem_base + s * T2_STAGE;
+                const uint32_t a_lo = a_hi + T2_ABYTES, b_hi = a_lo + T2_ABYTES, b_lo = b_hi + T2_BBYTES;
+#pragma unroll
+                for (int k = 0; k < T2_BK / 16; ++k) {
+                    const uint32_t ko = k * 16 * 128;
+                    const uint64_t dbh = make_desc(b_hi + ko, 4096, 1024), dbl = make_desc(b_lo + ko, 4096, 1024);
+#pragma unroll
+                    for (int acc = 0; acc < 2; ++acc) {
+                        if (acc == 1 && !two_acc) break;
+                        const uint32_t ao = acc * 8192 + ko;             // two 64-wide MN blocks per accumulator
+                        const uint64_t dah = make_desc(a_hi + ao, 4096, 1024), dal = make_desc(a_lo + ao, 4096, 1024);
+                        const uint32_t td = tmem_base + (uint32_t)(acc * 256);
+                        umma_bf16(td, dah, dbh, idesc, (kb | k) != 0);
+                        umma_bf16(td, dah, dbl, idesc, 1);
+                        umma_bf16(td, dal, dbh, idesc, 1);
+                    }
+                }
+                umma_commit(smem_u32(&sh->empty[s]));
+            }
+            umma_commit(smem_u32(&sh->tmem_full));
+        }
+    } else {
+        const int t = threadIdx.x - 32 * (kEpiWarps + 1);   // 0..255
+        // X tile: 32 rows x 64 float4; thread -> (q = t & 63, rows (t >> 6) + 4 i), 8 float4
+        const int qa = t & 63, ra = t >> 6;
+        const int ka = kbase + qa * 4;
+        const uint32_t offa = (uint32_t)(qa >> 4) * 4096 + (uint32_t)(((qa & 15) >> 1) << 4) + (uint32_t)(qa & 1) * 8;
+        // dY tile: 32 rows x (n_mma/4) float4, linear index t + 256 i; (row, q) fixed per thread -> computed once
+        const int qpr = n_mma >> 2;
+        constexpr int NB = 8;                                 // 32 * 64 / 256
+        int brow[NB], bq[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int idx = t + 256 * i;
+            brow[i] = idx / qpr;
+            bq[i] = idx - brow[i] * qpr;
+            if (brow[i] >= T2_BK) brow[i] = -1;
+        }
+        auto load_x = [&](int kb, int i) -> float4 {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t m = mbeg + (int64_t)kb * T2_BK + ra + 4 * i;
+            if (kb < nkb && m < mend && ka < Kv) {
+                const float* p = X + m * ldx + ka;
+                if (ka + 3 < Kv) v = ldg4(p);
+                else { v.x = __ldg(p); if (ka + 1 < Kv) v.y = __ldg(p + 1); if (ka + 2 < Kv) v.z = __ldg(p + 2); }
+            }
+            return v;
+        };
+        auto load_y = [&](int kb, int i) -> float4 {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (brow[i] < 0) return v;
+            const int64_t m = mbeg + (int64_t)kb * T2_BK + brow[i];
+            const int n = n0 + bq[i] * 4;
+            if (kb < nkb && m < mend && n < g.N) {
+                const float* p = g.dY + m * g.lddy + n;
+                if (n + 3 < g.N) v = ldg4(p);
+                else { v.x = __ldg(p); if (n + 1 < g.N) v.y = __ldg(p + 1); if (n + 2 < g.N) v.z = __ldg(p + 2); }
+            }
+            return v;
+        };
+        float4 xv[8], yv[NB];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = load_x(0, i);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) yv[i] = load_y(0, i);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % T2_STAGES;
+            const uint32_t sp = (kb / T2_STAGES) & 1;
+            mbar_wait(smem_u32(&sh->empty[s]), sp ^ 1);
+            const uint32_t a_hi = smem_base + s * T2_STAGE;
+            const uint32_t a_lo = a_hi + T2_ABYTES, b_hi = a_lo + T2_ABYTES, b_lo = b_hi + T2_BBYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kk = ra + 4 * i;
+                const uint32_t off = offa + (uint32_t)kk * 128;
+                // chunk swizzle: XOR the 16-byte chunk index with (row & 7)
+                const uint32_t sw = off ^ ((uint32_t)(kk & 7) << 4);
+                uint32_t h0, l0, h1, l1;
+                split2(xv[i].x, xv[i].y, h0, l0);
+                split2(xv[i].z, xv[i].w, h1, l1);
+                st_shared_v2(a_hi + sw, h0, h1);
+                st_shared_v2(a_lo + sw, l0, l1);
+                xv[i] = load_x(kb + 1, i);
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                if (brow[i] >= 0) {
+                    const int kk = brow[i], q = bq[i];
+                    const uint32_t off = (uint32_t)(q >> 4) * 4096 + (uint32_t)kk * 128 +
+                                         (uint32_t)((((q & 15) >> 1) ^ (kk & 7)) << 4) + (uint32_t)(q & 1) * 8;
+                    uint32_t h0, l0, h1, l1;
+                    split2(yv[i].x, yv[i].y, h0, l0);
+                    split2(yv[i].z, yv[i].w, h1, l1);
+                    st_shared_v2(b_hi + off, h0, h1);
+                    st_shared_v2(b_lo + off, l0, l1);
+                    yv[i] = load_y(kb + 1, i);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&sh->full[s]));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- weight pre-split
 // out[r, c] (hi/lo bf16, ld = ldo): r < R rows, c < Cpad columns.
 //   transpose = 0: out[r, c] = W[r, map(c)]  with map: c < K1pad -> c (valid if c < K1), else K1 + (c - K1pad) (valid if < K1+K2)
@@ -685,6 +890,53 @@ int tc_linear_bwd_weight(const float* dC, int64_t lddc, const float* A, int64_t 
     tc_tn_kernel<<<grid, kThreads, kTnSmemBytes, st>>>(a);
     SPGNN_LAUNCH_OK();
     reduce_splits((const float*)ws, splits, N, K, dW + k_off, lddw, st);
+    return SPGNN_OK;
+}
+
+
+static bool g_attr_set_tn2 = false;
+
+static void tn2_plan(int64_t M, int64_t N, int64_t K1, int64_t K2, int* BN, int* nt_n, int* nk1, int* nk2,
+                     int64_t* splits, int64_t* rows) {
+    tc::pick_bn((int)N, BN, nt_n);
+    *nk1 = (int)ceil_div(K1, 256);
+    *nk2 = K2 > 0 ? (int)ceil_div(K2, 256) : 0;
+    const int64_t tiles = (int64_t)(*nk1 + *nk2) * *nt_n;
+    int64_t want = ceil_div((int64_t)sm_count() * 4, tiles);
+    const int64_t max_by_rows = ceil_div(M, 1024);
+    if (want > max_by_rows) want = max_by_rows;
+    if (want > 512) want = 512;
+    if (want < 1) want = 1;
+    *rows = ceil_div(ceil_div(M, want), tc::T2_BK) * tc::T2_BK;
+    *splits = ceil_div(M, *rows);
+}
+
+int64_t tc_linear_bwd_weight2_ws_bytes(int64_t M, int64_t N, int64_t K1, int64_t K2) {
+    int BN, nt_n, nk1, nk2;
+    int64_t splits, rows;
+    tn2_plan(M, N, K1, K2, &BN, &nt_n, &nk1, &nk2, &splits, &rows);
+    return splits * N * (K1 + K2) * (int64_t)sizeof(float);
+}
+
+// dW[N, K1+K2] = dC[M,N]^T * [X1 | X2][M, K1+K2]
+int tc_linear_bwd_weight2(const float* dC, int64_t lddc, const float* X1, int64_t ldx1, int64_t K1, const float* X2,
+                          int64_t ldx2, int64_t K2, float* dW, int64_t lddw, int64_t M, int64_t N, void* ws,
+                          cudaStream_t st) {
+    if (!g_attr_set_tn2) {
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(tc::tc_tn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::T2_SMEM));
+        g_attr_set_tn2 = true;
+    }
+    tc::Tn2Args a{};
+    int64_t splits, rows;
+    tn2_plan(M, N, K1, X2 ? K2 : 0, &a.BN, &a.nt_n, &a.nk1, &a.nk2, &splits, &rows);
+    a.X1 = X1; a.ldx1 = ldx1; a.K1 = (int)K1; a.X2 = X2; a.ldx2 = ldx2; a.K2 = X2 ? (int)K2 : 0;
+    a.dY = dC; a.lddy = lddc; a.N = (int)N;
+    const int64_t Kt = K1 + (X2 ? K2 : 0);
+    a.out = (float*)ws; a.ldo = Kt; a.split_stride = N * Kt; a.M = M; a.rows_per_split = rows;
+    dim3 grid((unsigned)((a.nk1 + a.nk2) * a.nt_n), (unsigned)splits);
+    tc::tc_tn2_kernel<<<grid, tc::kThreads, tc::T2_SMEM, st>>>(a);
+    SPGNN_LAUNCH_OK();
+    reduce_splits((const float*)ws, splits, N, Kt, dW, lddw, st);
     return SPGNN_OK;
 }
 

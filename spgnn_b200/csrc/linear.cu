@@ -20,6 +20,10 @@ int64_t tc_linear_bwd_weight_ws_bytes(int64_t, int64_t, int64_t);
 int tc_linear_bwd_weight(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int64_t, int64_t,
                          int64_t, void*, cudaStream_t);
 
+int64_t tc_linear_bwd_weight2_ws_bytes(int64_t M, int64_t N, int64_t K1, int64_t K2);
+int tc_linear_bwd_weight2(const float*, int64_t, const float*, int64_t, int64_t, const float*, int64_t, int64_t, float*,
+                          int64_t, int64_t, int64_t, void*, cudaStream_t);
+
 static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 }  // namespace spgnn
 using namespace spgnn;
@@ -68,4 +72,34 @@ extern "C" int spgnn_linear_bwd_weight(const float* dC, int64_t lddc, const floa
     if (mode == 1 && al16(dC) && lddc % 4 == 0 && al16(A) && lda % 4 == 0)
         return tc_linear_bwd_weight(dC, lddc, A, lda, dW, lddw, k_off, M, N, K, ws, as_stream(stream));
     return simt_linear_bwd_weight(dC, lddc, A, lda, dW, lddw, k_off, M, N, K, ws, as_stream(stream));
+}
+
+extern "C" int64_t spgnn_linear_bwd_weight2_ws(int64_t M, int64_t N, int64_t K1, int64_t K2) {
+    int64_t m = simt_linear_bwd_weight_ws(M, N, K1);
+    const int64_t cand[4] = {K2 > 0 ? simt_linear_bwd_weight_ws(M, N, K2) : 0, tc_linear_bwd_weight2_ws_bytes(M, N, K1, K2),
+                             tc_linear_bwd_weight_ws_bytes(M, N, K1), K2 > 0 ? tc_linear_bwd_weight_ws_bytes(M, N, K2) : 0};
+    for (int i = 0; i < 4; ++i) m = cand[i] > m ? cand[i] : m;
+    return m;
+}
+
+extern "C" int spgnn_linear_bwd_weight2(const float* dC, int64_t lddc, const float* A1, int64_t lda1, int64_t K1,
+                                        const float* A2, int64_t lda2, int64_t K2, float* dW, int64_t lddw, int64_t M,
+                                        int64_t N, void* ws, int mode, void* stream) {
+    SPGNN_REQUIRE(dC && A1 && dW && ws && M > 0 && N > 0 && K1 > 0 && K2 >= 0, "linear_bwd_weight2: bad argument");
+    SPGNN_REQUIRE(lddc >= N && lda1 >= K1 && (!A2 || lda2 >= K2) && lddw >= K1 + (A2 ? K2 : 0),
+                  "linear_bwd_weight2: leading dimension too small");
+    const bool ok = al16(dC) && lddc % 4 == 0 && al16(A1) && lda1 % 4 == 0 && (!A2 || (al16(A2) && lda2 % 4 == 0));
+    // mode 2: experimental 256 x BN two-accumulator kernel (one pass over dC for both sources).  Measured on B200 it
+    // is latency-bound and slower than two passes of the 128x128 kernel (26 vs 19 ms on the 1063->1028 layer), so
+    // mode 1 runs the 128x128 kernel once per source.
+    if (mode == 2 && ok)
+        return tc_linear_bwd_weight2(dC, lddc, A1, lda1, K1, A2, lda2, K2, dW, lddw, M, N, ws, as_stream(stream));
+    if (mode == 1 && ok) {
+        int rc1 = tc_linear_bwd_weight(dC, lddc, A1, lda1, dW, lddw, 0, M, N, K1, ws, as_stream(stream));
+        if (rc1 || !A2 || K2 == 0) return rc1;
+        return tc_linear_bwd_weight(dC, lddc, A2, lda2, dW, lddw, K1, M, N, K2, ws, as_stream(stream));
+    }
+    int rc = simt_linear_bwd_weight(dC, lddc, A1, lda1, dW, lddw, 0, M, N, K1, ws, as_stream(stream));
+    if (rc || !A2 || K2 == 0) return rc;
+    return simt_linear_bwd_weight(dC, lddc, A2, lda2, dW, lddw, K1, M, N, K2, ws, as_stream(stream));
 }

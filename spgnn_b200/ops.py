@@ -121,12 +121,10 @@ class LinearFn(Function):
                                _key=("flops", 2.0 * M * N * K2))
         if ctx.needs_input_grad[2]:
             dW = empty_padded(N, K1 + K2, g.device)
-            for x, koff, K in ((x1, 0, K1), (x2, K1, K2)):
-                if x is None:
-                    continue
-                ws = torch.empty(max(int(L.linear_bwd_weight_ws(M, N, K)), 16), dtype=torch.uint8, device=g.device)
-                L.linear_bwd_weight(ptr(g), g.stride(0), ptr(x), x.stride(0), ptr(dW), dW.stride(0), koff, M, N, K,
-                                    ptr(ws), GEMM_MODE, stream(), _key=("flops", 2.0 * M * N * K))
+            ws = _ws(L.linear_bwd_weight2_ws(M, N, K1, K2), g.device)
+            L.linear_bwd_weight2(ptr(g), g.stride(0), ptr(x1), x1.stride(0), K1, ptr(x2),
+                                 x2.stride(0) if x2 is not None else 0, K2, ptr(dW), dW.stride(0), M, N, ptr(ws),
+                                 GEMM_MODE, stream(), _key=("flops", 2.0 * M * N * (K1 + K2)))
         if has_bias and ctx.needs_input_grad[3]:
             db = colsum(g)
         return dx1, dx2, dW, db, None, None

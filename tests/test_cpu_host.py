@@ -96,3 +96,25 @@ def test_models_construct_with_reference_settings_and_dgl_state_dict_names():
     from oracle import models as om
     kind, cfg = FULL_MODELS["st_pgat_spgnn_3"]
     assert set(om.GNNNet(kind, cfg).state_dict()) == set(sm.GATPositionSPGNNNet(**cfg).state_dict())
+
+
+def test_settings_loader_and_name_mapping(tmp_path):
+    from spgnn_b200.settings import PRESETS, Settings, get_callable_by_name
+    from spgnn_b200 import job_runner, models
+    f = tmp_path / "st_custom.py"
+    f.write_text("EXP_NAME = 'x'\nGCN_STEPS = 7\nlower = 1\nPOS_ENC_DIM = 39\n"
+                 "JOB_RUNNER_CLS = 'apps.airways.labeling_base.job_runner.GCNTrain'\n"
+                 "TEST_RUNNER_CLS = 'job_runner.GCNTestLSPE'\n"
+                 "MODEL = {'method': 'models.GATPositionLSPENet', 'fv_dim': 32}\n")
+    s = Settings(str(f))
+    assert s.GCN_STEPS == 7 and s.is_overridden("GCN_STEPS") and not hasattr(s, "lower")
+    assert s.TRAIN_BATCH_SIZE == 64 and not s.is_overridden("TRAIN_BATCH_SIZE")        # reference default
+    assert get_callable_by_name(s.JOB_RUNNER_CLS) is job_runner.GCNTrain               # absent module in the reference
+    assert get_callable_by_name(s.TEST_RUNNER_CLS) is job_runner.GCNTestSPGNN          # absent *LSPE names
+    assert get_callable_by_name(s.MODEL["method"]) is models.GATPositionSPGNNNet
+    assert get_callable_by_name("initializer.HeNorm") is job_runner.HeNorm
+    assert get_callable_by_name("torch.optim.SGD") is torch.optim.SGD
+    p = Settings("st_pgat_spgnn_3")
+    assert p.MODEL["pos_enc_dim"] == 39 and p.SAMPLING_RATE == 0.15 and set(PRESETS) >= {"st_gat_3", "st_gat_6_nr"}
+    cw = [p.CLASS_WEIGHTS[k] for k in sorted(p.CLASS_WEIGHTS.keys())][1:]
+    assert len(cw) == 22 and cw[0] == 0.2 and set(cw[1:]) == {0.8}                     # job_runner.py:1867
