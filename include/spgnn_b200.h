@@ -118,6 +118,42 @@ int64_t spgnn_linear_bwd_weight2_ws(int64_t M, int64_t N, int64_t K1, int64_t K2
 int spgnn_linear_bwd_weight2(const float* dC, int64_t lddc, const float* A1, int64_t lda1, int64_t K1,
                              const float* A2, int64_t lda2, int64_t K2, float* dW, int64_t lddw,
                              int64_t M, int64_t N, void* ws, int mode, void* stream);
+/* ------------------------------------------------------------------------------------
+ * Dense projection over "planes" operands — the production path of the same DGL projections (GATConv.fc / res_fc,
+ * gnn_out; models.py:301-314, 425-456, 1167-1170).
+ * Planes: an fp32-valued matrix X[rows, cols] stored as TWO bf16 matrices, X = hi + lo (|residual| <= 2^-18 |X|),
+ * both [rows, ld] row-major; the pointer passed is `hi`, lo = hi + plane_stride (elements).  ld and plane_stride must
+ * be multiples of 8 (16-byte rows), the base 16-byte aligned.  Same bytes as fp32, but the tensor cores consume them
+ * directly: operands go global -> shared by TMA and every product is hi*hi + hi*lo + lo*hi with fp32 accumulation
+ * (relative error ~1e-5).  The aggregation kernels (spgnn_gat_layer_*) and spgnn_split_planes PRODUCE planes, so no
+ * GEMM converts anything.  Weights stay fp32 in the ABI; they are split into `ws` once per call.
+ *   split_planes      : out planes [M, ldo] = dropout([x1 | x2], p) * 1/(1-p); mask = 16 hash bits per element of
+ *                       hash(seed, row * ceil(K/4) + col/4) (GATConv feat_drop on torch.cat([h_s,h_p]),
+ *                       models.py:431-435,477); p = 0 is a plain conversion.
+ *   planes_linear_fwd : C[M,N] fp32 (ldc) = [A1 | A2] * W[N, K1+K2 (ldw)]^T (+bias)(act)
+ *   planes_linear_bwd_input  : dA[M,K] fp32 (ldda) = dC[M,N] * W[N, k_off : k_off+K]
+ *   planes_linear_bwd_weight : dW[N, K1+K2] fp32 (lddw) = dC[M,N]^T * [X1 | X2]; reduction over the M nodes split
+ *                       into partial sums in ws, reduced in fixed order (deterministic).
+ * ---------------------------------------------------------------------------------- */
+int spgnn_split_planes(const float* x1, int64_t ld1, int64_t K1, const float* x2, int64_t ld2, int64_t K2,
+                       float p, uint64_t seed, uint16_t* out_hi, int64_t ldo, int64_t plane_stride,
+                       int64_t M, void* stream);
+int64_t spgnn_planes_linear_fwd_ws(int64_t N, int64_t K1, int64_t K2);
+int spgnn_planes_linear_fwd(const uint16_t* A1, int64_t lda1, int64_t ps1, int64_t K1,
+                            const uint16_t* A2, int64_t lda2, int64_t ps2, int64_t K2,
+                            const float* W, int64_t ldw, const float* bias, int act, float slope,
+                            float* C, int64_t ldc, int64_t M, int64_t N, void* ws, int64_t ws_bytes, void* stream);
+int64_t spgnn_planes_linear_bwd_input_ws(int64_t N, int64_t K);
+int spgnn_planes_linear_bwd_input(const uint16_t* dC, int64_t lddc, int64_t ps, const float* W, int64_t ldw,
+                                  int64_t k_off, float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K,
+                                  void* ws, int64_t ws_bytes, void* stream);
+int64_t spgnn_planes_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K1, int64_t K2);
+int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, int64_t psc,
+                                   const uint16_t* X1, int64_t ldx1, int64_t psx1, int64_t K1,
+                                   const uint16_t* X2, int64_t ldx2, int64_t psx2, int64_t K2,
+                                   float* dW, int64_t lddw, int64_t M, int64_t N,
+                                   void* ws, int64_t ws_bytes, void* stream);
+
 /* out[n] = sum_m X[m, n]  (bias gradients).  ws: spgnn_colsum_ws(N) bytes. */
 int64_t spgnn_colsum_ws(int64_t N);
 int spgnn_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* ws, void* stream);

@@ -1,0 +1,706 @@
+// TMA-fed tcgen05 GEMMs over "planes" operands (the production projection path).
+//
+// Planes: an fp32-valued matrix X[rows, cols] held as TWO bf16 matrices, X = hi + lo (|residual| <= 2^-18 |X|),
+// both [rows, ld] row-major, lo = hi + plane_stride.  Same bytes as fp32, but directly consumable by the tensor
+// cores: the product a*b is formed as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with fp32 accumulation in TMEM (three
+// kind::f16 UMMAs per k-step, relative error ~3*2^-18 per product — inside the 1e-4 parity bar, see gemm_tc.cu).
+// The kernels that PRODUCE activations (aggregation epilogues, spgnn_split_planes) write planes, so no GEMM converts
+// anything: operands go global -> shared by TMA (cp.async.bulk.tensor, SWIZZLE_128B) and shared -> tensor core by
+// UMMA descriptors; no register staging, several stages (64-96 KB each) in flight per SM.
+//
+//   nt_planes_kernel : C[M,N] fp32 = [A1|A2][M,K] * B[N,K]^T (+bias)(act).  A: activation planes (K-major boxes
+//                      64 x 128 x 2 planes), B: weight planes pre-split once per call.  Persistent over 128 x BN tiles,
+//                      two TMEM accumulator buffers (epilogue of tile i overlaps the MMAs of tile i+1).
+//                      Forward projection and dX = dY * W.
+//   tn_planes_kernel : D[p, q] = sum over nodes m of P[m, p] * Q[m, q]  (weight gradient dW = dY^T X, reduction over
+//                      the 1.2 M nodes, split across CTAs into partial sums reduced in fixed order).  Both operands
+//                      are activation planes read MN-major: TMA boxes of 64 columns x 32 nodes x 2 planes land as
+//                      [hi 4 KB][lo 4 KB] per 64-column block — exactly the SW128 MN-major UMMA layout, no transposition.
+//                      A CTA owns up to 4 P blocks (two M=128 accumulators sharing the Q tile) x up to 4 Q blocks
+//                      (N <= 256); blocks are enumerated across the concatenated sources ([X1 | X2]).
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMEM alloc + single-thread UMMA
+// issue, warp 5 single-thread TMA producer.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace spgnn {
+namespace tma {
+using namespace ptx;
+
+constexpr int BM = 128;
+constexpr int BK = 64;                         // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kMaxStages = 6;
+constexpr int kMaxBN = 256;
+constexpr int kABytes = BM * 128 * 2;          // hi + lo planes of the A tile: 32 KB
+constexpr int kStgLd = 36;                     // padded row of the per-warp 32x32 epilogue staging tile (floats)
+constexpr int kStgBytes = kEpiWarps * 32 * kStgLd * 4;
+constexpr int kSmemLimit = 232448;             // 227 KB opt-in limit per CTA
+constexpr int kNtFixed = 1024 /*align*/ + 256 /*barriers*/ + kStgBytes;
+
+struct NtMaps { CUtensorMap a1, a2, b; };
+struct NtArgs {
+    const float* bias; int act; float slope;
+    float* C; int64_t ldc;
+    int64_t M; int N;
+    int BN, nt_n; int64_t nt_m;
+    int kb1, kb2;
+    int stages, stage_bytes;
+};
+struct NtShared {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_constant__ NtMaps maps, const NtArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stages_bytes = g.stages * g.stage_bytes;
+    NtShared* sh = reinterpret_cast<NtShared*>(smem + stages_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(smem_u32(&sh->full[s]), 1);
+            mbar_init(smem_u32(&sh->empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&sh->tmem_full[b]), 1);
+            mbar_init(smem_u32(&sh->tmem_empty[b]), kEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 5 && lane == 0) {
+        prefetch_tmap(&maps.a1);
+        if (g.kb2 > 0) prefetch_tmap(&maps.a2);
+        prefetch_tmap(&maps.b);
+    }
+    if (warp == kEpiWarps) tmem_alloc(smem_u32(&sh->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    const int64_t n_tiles = g.nt_m * g.nt_n;
+    const int nkb = g.kb1 + g.kb2;
+
+    if (warp < kEpiWarps) {
+        // ===================================================== epilogue: TMEM -> registers -> smem staging -> global
+        int it = 0;
+        float* stg = reinterpret_cast<float*>(smem + stages_bytes + 256) + warp * (32 * kStgLd);
+        const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+        const bool plain = (g.act == SPGNN_ACT_NONE) && (g.bias == nullptr);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t par = (it >> 1) & 1;
+            const int64_t m0 = (tile / g.nt_n) * BM;
+            const int n0 = (int)(tile % g.nt_n) * g.BN;
+            const int ncols = min(g.BN, g.N - n0);
+            mbar_wait(smem_u32(&sh->tmem_full[buf]), par);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kMaxBN);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * kStgLd + 4 * j) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+                const int cc = (lane & 7) * 4;
+                const int col = n0 + c0 + cc;
+                const int rsub = lane >> 3;                                   // row within each group of 4
+                const int64_t row0 = m0 + warp * 32 + rsub;
+                float* q = g.C + row0 * g.ldc + col;
+                const int64_t qstep = 4 * g.ldc;
+                const int nrow = (int)max((int64_t)0, min((int64_t)8, (g.M - row0 + 3) / 4));
+                const float* sp = stg + rsub * kStgLd + cc;
+                if (plain && vec_ok && c0 + 32 <= ncols) {
+#pragma unroll
+                    for (int itr = 0; itr < 8; ++itr)
+                        if (itr < nrow) st4(q + itr * qstep, *reinterpret_cast<const float4*>(sp + itr * 4 * kStgLd));
+                } else {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.bias) {
+                        if (col + 0 < g.N) bv.x = __ldg(g.bias + col + 0);
+                        if (col + 1 < g.N) bv.y = __ldg(g.bias + col + 1);
+                        if (col + 2 < g.N) bv.z = __ldg(g.bias + col + 2);
+                        if (col + 3 < g.N) bv.w = __ldg(g.bias + col + 3);
+                    }
+                    const int nvalid = ncols - (c0 + cc);
+                    for (int itr = 0; itr < nrow; ++itr) {
+                        float4 x = *reinterpret_cast<const float4*>(sp + itr * 4 * kStgLd);
+                        x.x = act_fwd(x.x + bv.x, g.act, g.slope);
+                        x.y = act_fwd(x.y + bv.y, g.act, g.slope);
+                        x.z = act_fwd(x.z + bv.z, g.act, g.slope);
+                        x.w = act_fwd(x.w + bv.w, g.act, g.slope);
+                        float* qq = q + itr * qstep;
+                        if (vec_ok && nvalid >= 4) st4(qq, x);
+                        else {
+                            if (nvalid > 0) qq[0] = x.x;
+                            if (nvalid > 1) qq[1] = x.y;
+                            if (nvalid > 2) qq[2] = x.z;
+                            if (nvalid > 3) qq[3] = x.w;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sh->tmem_empty[buf]));
+        }
+    } else if (warp == kEpiWarps) {
+        // ===================================================== UMMA issuer (one elected thread)
+        if (lane == 0) {
+            int it = 0;
+            uint32_t kcount = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t par = (it >> 1) & 1;
+                const int n0 = (int)(tile % g.nt_n) * g.BN;
+                const int ncols = min(g.BN, g.N - n0);
+                const int n_mma = (ncols + 15) & ~15;
+                const uint32_t idesc = make_idesc(n_mma, false);
+                mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);     // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kMaxBN);
+                for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                    const int s = kcount % g.stages;
+                    const uint32_t sp = (kcount / g.stages) & 1;
+                    mbar_wait(smem_u32(&sh->full[s]), sp);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_base + s * g.stage_bytes;
+                    const uint32_t a_lo = a_hi + BM * 128;
+                    const uint32_t b_hi = a_hi + kABytes;
+                    const uint32_t b_lo = b_hi + g.BN * 128;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t ko = k * 32;      // 16 bf16 = 32 bytes along the swizzled row
+                        const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                        const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                        umma_bf16(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, dah, dbl, idesc, 1);
+                        umma_bf16(tmem_d, dal, dbh, idesc, 1);
+                    }
+                    umma_commit(smem_u32(&sh->empty[s]));      // frees the smem stage when these UMMAs retire
+                }
+                umma_commit(smem_u32(&sh->tmem_full[buf]));    // accumulator complete -> epilogue
+            }
+        }
+    } else if (lane == 0) {
+        // ===================================================== TMA producer (one thread)
+        uint32_t kcount = 0;
+        const uint32_t tx = (uint32_t)g.stage_bytes;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m0 = (int)((tile / g.nt_n) * BM);
+            const int n0 = (int)(tile % g.nt_n) * g.BN;
+            for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                const int s = kcount % g.stages;
+                const uint32_t sp = (kcount / g.stages) & 1;
+                mbar_wait(smem_u32(&sh->empty[s]), sp ^ 1);
+                const uint32_t bar = smem_u32(&sh->full[s]);
+                mbar_expect_tx(bar, tx);
+                const uint32_t dst = smem_base + s * g.stage_bytes;
+                if (kb < g.kb1) tma_load_3d(dst, &maps.a1, bar, kb * BK, m0, 0);
+                else tma_load_3d(dst, &maps.a2, bar, (kb - g.kb1) * BK, m0, 0);
+                tma_load_3d(dst + kABytes, &maps.b, bar, kb * BK, n0, 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- TN kernel (dW)
+constexpr int T_BK = 32;                       // nodes per stage
+constexpr int T_BLK = 2 * T_BK * 128;          // one 64-column block, hi + lo planes: 8 KB
+constexpr int T_STAGE = 8 * T_BLK;             // up to 4 P blocks + 4 Q blocks: 64 KB
+constexpr int T_STAGES = 3;
+constexpr int T_SMEM = T_STAGES * T_STAGE + 1024 + 256;
+
+struct TnMaps { CUtensorMap p[2], q[2]; };
+struct TnArgs {
+    int p_cols[2], q_cols[2];                  // columns of each source (0 = absent)
+    int p_off[2], q_off[2];                    // first output index of each source
+    float* out; int64_t ldo; int64_t split_stride; int transposed;   // transposed: out[q * ldo + p], else out[p * ldo + q]
+    int64_t M; int64_t rows_per_split;
+    int npb, nqb;                              // 64-column blocks over the concatenated sources
+    int np_tiles, nq_tiles;
+};
+struct TnShared {
+    uint64_t full[T_STAGES];
+    uint64_t empty[T_STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_base;
+};
+struct Blk { int src, col0, valid; };
+__device__ __forceinline__ Blk blk_of(const int (&cols)[2], int b) {
+    const int nb0 = (cols[0] + 63) >> 6;
+    Blk r;
+    r.src = b >= nb0;
+    r.col0 = (r.src ? b - nb0 : b) << 6;
+    r.valid = min(64, cols[r.src] - r.col0);
+    return r;
+}
+__device__ __forceinline__ void tile_range(int nb, int tiles, int t, int& first, int& count) {
+    const int base = nb / tiles, rem = nb % tiles;
+    first = t * base + min(t, rem);
+    count = base + (t < rem ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_constant__ TnMaps maps, const TnArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    TnShared* sh = reinterpret_cast<TnShared*>(smem + T_STAGES * T_STAGE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T_STAGES; ++s) {
+            mbar_init(smem_u32(&sh->full[s]), 1);
+            mbar_init(smem_u32(&sh->empty[s]), 1);
+        }
+        mbar_init(smem_u32(&sh->tmem_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == 5 && lane == 0) {
+        prefetch_tmap(&maps.p[0]);
+        prefetch_tmap(&maps.q[0]);
+        if (g.p_cols[1] > 0) prefetch_tmap(&maps.p[1]);
+        if (g.q_cols[1] > 0) prefetch_tmap(&maps.q[1]);
+    }
+    if (warp == kEpiWarps) tmem_alloc(smem_u32(&sh->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    const int tp = blockIdx.x / g.nq_tiles, tq = blockIdx.x % g.nq_tiles;
+    int pb0, npb, qb0, nqb;
+    tile_range(g.npb, g.np_tiles, tp, pb0, npb);
+    tile_range(g.nqb, g.nq_tiles, tq, qb0, nqb);
+    const int64_t mbeg = (int64_t)blockIdx.y * g.rows_per_split;
+    const int64_t mend = min(g.M, mbeg + g.rows_per_split);
+    const int nkb = mend > mbeg ? (int)((mend - mbeg + T_BK - 1) / T_BK) : 0;
+    const int nacc = npb > 2 ? 2 : 1;
+    const Blk qlast = blk_of(g.q_cols, qb0 + nqb - 1);
+    const int n_mma = 64 * (nqb - 1) + ((qlast.valid + 15) & ~15);
+
+    if (warp < kEpiWarps) {
+        // ===================================================== epilogue: TMEM -> partial sums in the workspace
+        mbar_wait(smem_u32(&sh->tmem_full), 0);
+        tc_fence_after();
+        float* obase = g.out + (int64_t)blockIdx.y * g.split_stride;
+        for (int acc = 0; acc < nacc; ++acc) {
+            const int pbi = acc * 2 + (warp >> 1);                 // P block of this warp's 32 lanes
+            if (pbi >= npb) continue;
+            const Blk pb = blk_of(g.p_cols, pb0 + pbi);
+            const int pin = (warp & 1) * 32 + lane;                // column within the block
+            const bool pok = pin < pb.valid;
+            const int64_t pidx = g.p_off[pb.src] + pb.col0 + pin;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
+            for (int c0 = 0; c0 < n_mma; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                const Blk qb = blk_of(g.q_cols, qb0 + (c0 >> 6));
+                const int qin = c0 & 63;
+                const int nv = min(16, qb.valid - qin);
+                if (pok && nv > 0) {
+                    const int64_t qidx = g.q_off[qb.src] + qb.col0 + qin;
+                    if (g.transposed) {
+                        float* o = obase + qidx * g.ldo + pidx;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nv) o[(int64_t)j * g.ldo] = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
+                    } else {
+                        float* o = obase + pidx * g.ldo + qidx;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nv) o[j] = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
+                    }
+                }
+            }
+        }
+    } else if (warp == kEpiWarps) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(n_mma, true);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % T_STAGES;
+                const uint32_t sp = (kb / T_STAGES) & 1;
+                mbar_wait(smem_u32(&sh->full[s]), sp);
+                tc_fence_after();
+                const uint32_t p_base = smem_base + s * T_STAGE;
+                const uint32_t q_base = p_base + 4 * T_BLK;
+#pragma unroll
+                for (int k = 0; k < T_BK / 16; ++k) {
+                    const uint32_t ko = k * 16 * 128;            // 16 node rows of 128 B
+                    // MN-major SW128: 64-column blocks T_BLK apart (LBO), 8-row groups 1 KB apart (SBO)
+                    const uint64_t dbh = make_desc(q_base + ko, T_BLK, 1024);
+                    const uint64_t dbl = make_desc(q_base + T_BLK / 2 + ko, T_BLK, 1024);
+                    for (int acc = 0; acc < nacc; ++acc) {
+                        const uint32_t ao = p_base + acc * 2 * T_BLK + ko;
+                        const uint64_t dah = make_desc(ao, T_BLK, 1024), dal = make_desc(ao + T_BLK / 2, T_BLK, 1024);
+                        const uint32_t td = tmem_base + (uint32_t)(acc * 256);
+                        umma_bf16(td, dah, dbh, idesc, (kb | k) != 0);
+                        umma_bf16(td, dah, dbl, idesc, 1);
+                        umma_bf16(td, dal, dbh, idesc, 1);
+                    }
+                }
+                umma_commit(smem_u32(&sh->empty[s]));
+            }
+            umma_commit(smem_u32(&sh->tmem_full));   // with nkb == 0 nothing is pending: arrives immediately
+        }
+    } else if (lane == 0) {
+        const uint32_t tx = (uint32_t)(npb + nqb) * T_BLK;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % T_STAGES;
+            const uint32_t sp = (kb / T_STAGES) & 1;
+            mbar_wait(smem_u32(&sh->empty[s]), sp ^ 1);
+            const uint32_t bar = smem_u32(&sh->full[s]);
+            mbar_expect_tx(bar, tx);
+            const uint32_t dst = smem_base + s * T_STAGE;
+            const int m = (int)(mbeg + (int64_t)kb * T_BK);
+            for (int i = 0; i < npb; ++i) {
+                const Blk b = blk_of(g.p_cols, pb0 + i);
+                tma_load_3d(dst + i * T_BLK, &maps.p[b.src], bar, b.col0, m, 0);
+            }
+            for (int i = 0; i < nqb; ++i) {
+                const Blk b = blk_of(g.q_cols, qb0 + i);
+                tma_load_3d(dst + (4 + i) * T_BLK, &maps.q[b.src], bar, b.col0, m, 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- plane producers
+__device__ __forceinline__ uint64_t chunk_hash(uint64_t seed, uint64_t idx) { return mix64(seed ^ (idx * 0xD1B54A32D192ED03ull)); }
+
+// out planes [M, ldo] <- dropout([x1 | x2]) (scaled by 1/(1-p)); one thread per 4-column chunk of the concatenation.
+// Mask: 16 hash bits per element, chunk index = row * nchunks + chunk (the convention of every plane producer).
+__global__ void split_planes_kernel(const float* __restrict__ x1, int64_t ld1, int K1, const float* __restrict__ x2,
+                                    int64_t ld2, int K2, uint32_t thr, float scale, uint64_t seed,
+                                    __nv_bfloat16* __restrict__ hi, int64_t ldo, int64_t ps, int64_t M) {
+    const int K = K1 + K2;
+    const int nch = (K + 3) >> 2;
+    const int64_t total = M * nch;
+    const bool v1 = (ld1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x1) & 15) == 0);
+    const bool v2 = x2 && (ld2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x2) & 15) == 0) && (K1 % 4 == 0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / nch;
+        const int c = (int)(i - r * nch) * 4;
+        float v[4];
+        if (c + 3 < K1 && v1) {
+            const float4 t = ldg4(x1 + r * ld1 + c);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else if (c >= K1 && c + 3 < K && v2) {
+            const float4 t = ldg4(x2 + r * ld2 + (c - K1));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cc = c + j;
+                v[j] = cc < K1 ? __ldg(x1 + r * ld1 + cc) : (cc < K ? __ldg(x2 + r * ld2 + (cc - K1)) : 0.f);
+            }
+        }
+        if (thr) {
+            const uint64_t h = chunk_hash(seed, (uint64_t)i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = ((uint32_t)(h >> (16 * j)) & 0xFFFFu) >= thr ? v[j] * scale : 0.f;
+        }
+        uint32_t h0, l0, h1, l1;
+        split2(v[0], v[1], h0, l0);
+        split2(v[2], v[3], h1, l1);
+        __nv_bfloat16* o = hi + r * ldo + c;
+        *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(o + ps) = make_uint2(l0, l1);
+    }
+}
+
+// weight planes.  transpose = 0: out[r, c] = W[r, map(c)], map: c < K1pad -> c (valid if c < K1), else
+// K1 + (c - K1pad) (valid if < K1 + K2).  transpose = 1: out[r, c] = W[c, k_off + r] (c < Nvalid).
+__global__ void split_weight_kernel(const float* __restrict__ W, int64_t ldw, int transpose, int64_t k_off, int R,
+                                    int Cpad, int K1, int K1pad, int K2, int Nvalid, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int64_t ldo) {
+    const int64_t total = (int64_t)R * Cpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / Cpad), c = (int)(i - (int64_t)r * Cpad);
+        float v = 0.f;
+        if (!transpose) {
+            if (c < K1pad) { if (c < K1) v = W[(int64_t)r * ldw + c]; }
+            else if (c - K1pad < K2) v = W[(int64_t)r * ldw + K1 + (c - K1pad)];
+        } else if (c < Nvalid) {
+            v = W[(int64_t)c * ldw + k_off + r];
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[(int64_t)r * ldo + c] = h;
+        lo[(int64_t)r * ldo + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// planes [rows, cols] (ld elements between rows, ps elements between the hi and lo plane) -> 3-D map {cols, rows, 2}
+static int make_planes_map(CUtensorMap* m, const void* hi, int64_t rows, int64_t cols, int64_t ld, int64_t ps,
+                           int box_cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    SPGNN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+    SPGNN_REQUIRE(((uintptr_t)hi & 15) == 0 && (ld * 2) % 16 == 0 && (ps * 2) % 16 == 0 && rows > 0 && cols > 0,
+                  "planes operand: base must be 16-byte aligned, ld (%lld) and plane stride (%lld) multiples of 8",
+                  (long long)ld, (long long)ps);
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ps * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 2};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(hi), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SPGNN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld ps=%lld", (int)r,
+                  (long long)rows, (long long)cols, (long long)ld, (long long)ps);
+    return SPGNN_OK;
+}
+
+static inline int round_up(int64_t x, int m) { return (int)((x + m - 1) / m * m); }
+
+// tile width: as few n-tiles as possible, equal widths, multiple of 16
+static void pick_bn(int N, int* BN, int* nt) {
+    const int n16 = round_up(N, 16);
+    *nt = (n16 + kMaxBN - 1) / kMaxBN;
+    *BN = round_up((n16 + *nt - 1) / *nt, 16);
+}
+
+static unsigned split_grid(int64_t total) {
+    const int64_t want = ceil_div(total, 256), cap = (int64_t)sm_count() * 16;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+// C = [A1|A2] * Bplanes^T with Bplanes [N, ldb] already split (hi at Bhi, lo at Bhi + N*ldb)
+static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t K1, const __nv_bfloat16* A2,
+                     int64_t lda2, int64_t ps2, int64_t K2, const __nv_bfloat16* Bhi, int64_t ldb, const float* bias,
+                     int act, float slope, float* C, int64_t ldc, int64_t M, int64_t N, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr = true;
+    }
+    NtMaps maps;
+    NtArgs a{};
+    pick_bn((int)N, &a.BN, &a.nt_n);
+    int rc = make_planes_map(&maps.a1, A1, M, K1, lda1, ps1, BK, BM);
+    if (rc) return rc;
+    if (A2 && K2 > 0) {
+        rc = make_planes_map(&maps.a2, A2, M, K2, lda2, ps2, BK, BM);
+        if (rc) return rc;
+    } else {
+        maps.a2 = maps.a1;
+    }
+    rc = make_planes_map(&maps.b, Bhi, N, ldb, ldb, N * ldb, BK, a.BN);
+    if (rc) return rc;
+    a.bias = bias; a.act = act; a.slope = slope; a.C = C; a.ldc = ldc; a.M = M; a.N = (int)N;
+    a.nt_m = ceil_div(M, BM);
+    a.kb1 = (int)ceil_div(K1, BK);
+    a.kb2 = (A2 && K2 > 0) ? (int)ceil_div(K2, BK) : 0;
+    a.stage_bytes = kABytes + a.BN * 256;
+    a.stages = (kSmemLimit - kNtFixed) / a.stage_bytes;
+    if (a.stages > kMaxStages) a.stages = kMaxStages;
+    const int64_t tiles = a.nt_m * a.nt_n;
+    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    nt_planes_kernel<<<grid, kThreads, kSmemLimit, st>>>(maps, a);
+    SPGNN_LAUNCH_OK();
+    return SPGNN_OK;
+}
+
+}  // namespace tma
+}  // namespace spgnn
+
+using namespace spgnn;
+using namespace spgnn::tma;
+
+namespace spgnn {
+void reduce_splits(const float* ws, int64_t splits, int64_t N, int64_t K, float* out, int64_t ldo, cudaStream_t st);
+}
+
+extern "C" int spgnn_split_planes(const float* x1, int64_t ld1, int64_t K1, const float* x2, int64_t ld2, int64_t K2,
+                                  float p, uint64_t seed, uint16_t* out_hi, int64_t ldo, int64_t plane_stride,
+                                  int64_t M, void* stream) {
+    SPGNN_REQUIRE(x1 && out_hi && M > 0 && K1 > 0 && K2 >= 0 && (K2 == 0 || x2), "split_planes: bad argument");
+    SPGNN_REQUIRE(ldo % 4 == 0 && ldo >= ((K1 + K2 + 3) / 4) * 4 && plane_stride % 4 == 0 && ((uintptr_t)out_hi & 7) == 0,
+                  "split_planes: output ld (%lld) must be a multiple of 4 covering the padded row", (long long)ldo);
+    SPGNN_REQUIRE(p >= 0.f && p < 1.f, "split_planes: dropout p");
+    const uint32_t thr = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    const int64_t total = M * ((K1 + K2 + 3) / 4);
+    split_planes_kernel<<<split_grid(total), 256, 0, as_stream(stream)>>>(
+        x1, ld1, (int)K1, K2 > 0 ? x2 : nullptr, ld2, (int)K2, thr, scale, seed,
+        reinterpret_cast<__nv_bfloat16*>(out_hi), ldo, plane_stride, M);
+    SPGNN_LAUNCH_OK();
+    return SPGNN_OK;
+}
+
+extern "C" int64_t spgnn_planes_linear_fwd_ws(int64_t N, int64_t K1, int64_t K2) {
+    const int64_t kp = round_up(K1, BK) + (K2 > 0 ? round_up(K2, BK) : 0);
+    return 2 * N * kp * (int64_t)sizeof(__nv_bfloat16) + 256;
+}
+
+extern "C" int spgnn_planes_linear_fwd(const uint16_t* A1, int64_t lda1, int64_t ps1, int64_t K1, const uint16_t* A2,
+                                       int64_t lda2, int64_t ps2, int64_t K2, const float* W, int64_t ldw,
+                                       const float* bias, int act, float slope, float* C, int64_t ldc, int64_t M,
+                                       int64_t N, void* ws, int64_t ws_bytes, void* stream) {
+    SPGNN_REQUIRE(A1 && W && C && ws && M > 0 && N > 0 && K1 > 0 && K2 >= 0, "planes_linear_fwd: bad argument");
+    if (!A2) K2 = 0;
+    SPGNN_REQUIRE(ldw >= K1 + K2 && ldc >= N, "planes_linear_fwd: leading dimension smaller than row length");
+    SPGNN_REQUIRE(ws_bytes >= spgnn_planes_linear_fwd_ws(N, K1, K2), "planes_linear_fwd: workspace too small");
+    SPGNN_REQUIRE(M < (1ll << 31) && N < (1 << 24), "planes_linear_fwd: shape too large");
+    cudaStream_t st = as_stream(stream);
+    const int k1p = round_up(K1, BK), k2p = K2 > 0 ? round_up(K2, BK) : 0;
+    const int64_t ldb = k1p + k2p;
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(((uintptr_t)ws + 127) & ~(uintptr_t)127);
+    split_weight_kernel<<<split_grid(N * ldb), 256, 0, st>>>(W, ldw, 0, 0, (int)N, (int)ldb, (int)K1, k1p, (int)K2, 0,
+                                                             hi, hi + N * ldb, ldb);
+    SPGNN_LAUNCH_OK();
+    return launch_nt(reinterpret_cast<const __nv_bfloat16*>(A1), lda1, ps1, K1,
+                     reinterpret_cast<const __nv_bfloat16*>(A2), lda2, ps2, K2, hi, ldb, bias, act, slope, C, ldc, M, N,
+                     st);
+}
+
+extern "C" int64_t spgnn_planes_linear_bwd_input_ws(int64_t N, int64_t K) {
+    return 2 * K * (int64_t)round_up(N, BK) * 2 + 256;
+}
+
+// dA[M, K] = dC[M, N] * W[N, k_off : k_off + K]:  NT GEMM with B = (W^T)[K, N] pre-split
+extern "C" int spgnn_planes_linear_bwd_input(const uint16_t* dC, int64_t lddc, int64_t ps, const float* W, int64_t ldw,
+                                             int64_t k_off, float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K,
+                                             void* ws, int64_t ws_bytes, void* stream) {
+    SPGNN_REQUIRE(dC && W && dA && ws && M > 0 && N > 0 && K > 0, "planes_linear_bwd_input: bad argument");
+    SPGNN_REQUIRE(ldw >= k_off + K && ldda >= K, "planes_linear_bwd_input: leading dimension too small");
+    SPGNN_REQUIRE(ws_bytes >= spgnn_planes_linear_bwd_input_ws(N, K), "planes_linear_bwd_input: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const int np = round_up(N, BK);
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(((uintptr_t)ws + 127) & ~(uintptr_t)127);
+    split_weight_kernel<<<split_grid(K * np), 256, 0, st>>>(W, ldw, 1, k_off, (int)K, np, 0, 0, 0, (int)N, hi,
+                                                            hi + K * np, np);
+    SPGNN_LAUNCH_OK();
+    return launch_nt(reinterpret_cast<const __nv_bfloat16*>(dC), lddc, ps, N, nullptr, 0, 0, 0, hi, np, nullptr, 0, 0.f,
+                     dA, ldda, M, K, st);
+}
+
+namespace {
+struct TnPlan {
+    bool swap;                 // false: P = X (k), Q = dC (n) -> out[q][p];  true: P = dC, Q = X -> out[p][q]
+    int npb, nqb, np_tiles, nq_tiles;
+    int64_t splits, rows;
+};
+int blocks_of(int64_t c0, int64_t c1) { return (int)(ceil_div(c0, 64) + (c1 > 0 ? ceil_div(c1, 64) : 0)); }
+int64_t load_cost(int npb, int nqb) {
+    const int pt = (int)ceil_div(npb, 4), qt = (int)ceil_div(nqb, 4);
+    return (int64_t)qt * npb + (int64_t)pt * nqb;          // 64-column block loads per k-step, all tiles
+}
+TnPlan tn_plan(int64_t M, int64_t N, int64_t K1, int64_t K2) {
+    TnPlan t;
+    const int xb = blocks_of(K1, K2), yb = blocks_of(N, 0);
+    t.swap = load_cost(yb, xb) < load_cost(xb, yb);
+    t.npb = t.swap ? yb : xb;
+    t.nqb = t.swap ? xb : yb;
+    t.np_tiles = (int)ceil_div(t.npb, 4);
+    t.nq_tiles = (int)ceil_div(t.nqb, 4);
+    const int64_t tiles = (int64_t)t.np_tiles * t.nq_tiles;
+    int64_t want = sm_count() / tiles;
+    const int64_t max_by_rows = ceil_div(M, 512);
+    if (want > max_by_rows) want = max_by_rows;
+    if (want < 1) want = 1;
+    t.rows = ceil_div(ceil_div(M, want), T_BK) * T_BK;
+    t.splits = ceil_div(M, t.rows);
+    return t;
+}
+}  // namespace
+
+extern "C" int64_t spgnn_planes_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K1, int64_t K2) {
+    const TnPlan t = tn_plan(M, N, K1, K2);
+    return t.splits * N * (K1 + K2) * (int64_t)sizeof(float) + 256;
+}
+
+// dW[N, K1+K2] (lddw) = dC[M, N]^T * [X1 | X2][M, K1+K2], every operand in planes form
+extern "C" int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, int64_t psc, const uint16_t* X1,
+                                              int64_t ldx1, int64_t psx1, int64_t K1, const uint16_t* X2, int64_t ldx2,
+                                              int64_t psx2, int64_t K2, float* dW, int64_t lddw, int64_t M, int64_t N,
+                                              void* ws, int64_t ws_bytes, void* stream) {
+    SPGNN_REQUIRE(dC && X1 && dW && ws && M > 0 && N > 0 && K1 > 0 && K2 >= 0, "planes_linear_bwd_weight: bad argument");
+    if (!X2) K2 = 0;
+    SPGNN_REQUIRE(lddw >= K1 + K2, "planes_linear_bwd_weight: leading dimension too small");
+    SPGNN_REQUIRE(ws_bytes >= spgnn_planes_linear_bwd_weight_ws(M, N, K1, K2), "planes_linear_bwd_weight: workspace too small");
+    SPGNN_REQUIRE(M < (1ll << 31), "planes_linear_bwd_weight: too many rows");
+    static bool attr = false;
+    if (!attr) {
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(tn_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+        attr = true;
+    }
+    cudaStream_t st = as_stream(stream);
+    const TnPlan t = tn_plan(M, N, K1, K2);
+    const int64_t Kt = K1 + K2;
+    TnMaps maps;
+    TnArgs a{};
+    CUtensorMap mx1, mx2, my;
+    int rc = make_planes_map(&mx1, X1, M, K1, ldx1, psx1, 64, T_BK);
+    if (rc) return rc;
+    mx2 = mx1;
+    if (K2 > 0) {
+        rc = make_planes_map(&mx2, X2, M, K2, ldx2, psx2, 64, T_BK);
+        if (rc) return rc;
+    }
+    rc = make_planes_map(&my, dC, M, N, lddc, psc, 64, T_BK);
+    if (rc) return rc;
+    if (!t.swap) {
+        maps.p[0] = mx1; maps.p[1] = mx2; maps.q[0] = my; maps.q[1] = my;
+        a.p_cols[0] = (int)K1; a.p_cols[1] = (int)K2; a.q_cols[0] = (int)N; a.q_cols[1] = 0;
+        a.p_off[0] = 0; a.p_off[1] = (int)K1; a.q_off[0] = 0; a.q_off[1] = 0;
+        a.transposed = 1;                       // out[n (q)][k (p)]
+    } else {
+        maps.p[0] = my; maps.p[1] = my; maps.q[0] = mx1; maps.q[1] = mx2;
+        a.p_cols[0] = (int)N; a.p_cols[1] = 0; a.q_cols[0] = (int)K1; a.q_cols[1] = (int)K2;
+        a.p_off[0] = 0; a.p_off[1] = 0; a.q_off[0] = 0; a.q_off[1] = (int)K1;
+        a.transposed = 0;                       // out[n (p)][k (q)]
+    }
+    a.out = reinterpret_cast<float*>(((uintptr_t)ws + 127) & ~(uintptr_t)127);
+    a.ldo = Kt; a.split_stride = N * Kt; a.M = M; a.rows_per_split = t.rows;
+    a.npb = t.npb; a.nqb = t.nqb; a.np_tiles = t.np_tiles; a.nq_tiles = t.nq_tiles;
+    dim3 grid((unsigned)(t.np_tiles * t.nq_tiles), (unsigned)t.splits);
+    tn_planes_kernel<<<grid, kThreads, T_SMEM, st>>>(maps, a);
+    SPGNN_LAUNCH_OK();
+    reduce_splits(a.out, t.splits, N, Kt, dW, lddw, st);
+    return SPGNN_OK;
+}
