@@ -129,15 +129,17 @@ int spgnn_linear_bwd_weight2(const float* dC, int64_t lddc, const float* A1, int
  * GEMM converts anything.  Weights stay fp32 in the ABI; they are split into `ws` once per call.
  *   split_planes      : out planes [M, ldo] = dropout([x1 | x2], p) * 1/(1-p); mask = 16 hash bits per element of
  *                       hash(seed, row * ceil(K/4) + col/4) (GATConv feat_drop on torch.cat([h_s,h_p]),
- *                       models.py:431-435,477); p = 0 is a plain conversion.
+ *                       models.py:431-435,477); p = 0 is a plain conversion.  When the result is one part of a
+ *                       larger concatenation, concat_chunks = ceil(K_concat/4) and chunk_off = first column / 4
+ *                       place it in the consumer's mask numbering (0, 0 = the tensor stands alone).
  *   planes_linear_fwd : C[M,N] fp32 (ldc) = [A1 | A2] * W[N, K1+K2 (ldw)]^T (+bias)(act)
  *   planes_linear_bwd_input  : dA[M,K] fp32 (ldda) = dC[M,N] * W[N, k_off : k_off+K]
  *   planes_linear_bwd_weight : dW[N, K1+K2] fp32 (lddw) = dC[M,N]^T * [X1 | X2]; reduction over the M nodes split
  *                       into partial sums in ws, reduced in fixed order (deterministic).
  * ---------------------------------------------------------------------------------- */
 int spgnn_split_planes(const float* x1, int64_t ld1, int64_t K1, const float* x2, int64_t ld2, int64_t K2,
-                       float p, uint64_t seed, uint16_t* out_hi, int64_t ldo, int64_t plane_stride,
-                       int64_t M, void* stream);
+                       float p, uint64_t seed, int64_t concat_chunks, int64_t chunk_off,
+                       uint16_t* out_hi, int64_t ldo, int64_t plane_stride, int64_t M, void* stream);
 int64_t spgnn_planes_linear_fwd_ws(int64_t N, int64_t K1, int64_t K2);
 int spgnn_planes_linear_fwd(const uint16_t* A1, int64_t lda1, int64_t ps1, int64_t K1,
                             const uint16_t* A2, int64_t lda2, int64_t ps2, int64_t K2,
@@ -190,6 +192,54 @@ int spgnn_gat_agg_bwd(const float* g_out, int64_t ldg, const float* out, int64_t
                       const int32_t* out_ptr, const int32_t* out_dst, const int32_t* out_slot,
                       int64_t N, int64_t H, int64_t F,
                       float* dY, float* dxres, float* g_ws, float* ds_ws, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * GAT layer of the planes pipeline: the same fused edge-softmax + aggregation + residual + bias + activation
+ * (+ head mean) as spgnn_gat_agg_*, but the layer OUTPUT is written as planes — one copy per consumer, with that
+ * consumer's feat_drop mask already applied (GATConv.feat_drop on torch.cat([h_s,h_p]), models.py:431-456,476-482) —
+ * and the backward reads the masked gradient contributions of every consumer (the dX of the next projections)
+ * directly and writes dY as planes for the dX / dW projections.  torch.cat, dropout and the fp32 -> bf16 split never
+ * make a pass of their own over HBM.  The bias gradient (column sum of g) comes out of the same backward kernel.
+ *   Y  [N, ldy] fp32: cols [0,HF) z; [res_off, res_off+HF) residual projection (res_mode 1); el at el_off+h,
+ *      er at er_off+h.  res_mode 0 = no residual, 1 = linear (identity residuals use spgnn_gat_agg_*).
+ *   forward : att [E,H] out; `out` fp32 [N, ldo] optional; sinks[n_sinks] planes copies of the output
+ *             (width HF, or F when mean_heads).  Dropout mask of a sink = 16 hash bits per element of
+ *             hash(seed, row * concat_chunks + chunk_off + col/4) — the convention of spgnn_split_planes, with
+ *             concat_chunks = ceil(K_concat/4) of the consumer's concatenated input and chunk_off = this tensor's
+ *             first column in it / 4.
+ *   backward: gsrc[n_gsrc] fp32 gradient contributions (pointer already at this tensor's first column inside the
+ *             consumer's dX), each masked with the consumer's dropout as above; outputs dY planes [N, dY_ld] (same
+ *             column layout as Y), ds_ws [E*H] scratch, g_ws fp32 [N,HF] (only when res_mode 0),
+ *             dbias [HF] (optional; needs dbias_ws of spgnn_gat_layer_dbias_ws bytes).  Pre-activations are
+ *             recomputed from Y, so the forward output need not be kept.
+ * ---------------------------------------------------------------------------------- */
+typedef struct spgnn_sink {
+    uint16_t* hi; int64_t ld; int64_t plane_stride;
+    int64_t concat_chunks; int64_t chunk_off;
+    float drop_p; uint32_t reserved; uint64_t seed;
+} spgnn_sink;
+typedef struct spgnn_gsrc {
+    const float* g; int64_t ld;
+    int64_t concat_chunks; int64_t chunk_off;
+    float drop_p; uint32_t reserved; uint64_t seed;
+} spgnn_gsrc;
+typedef struct spgnn_gat_layer {
+    const int32_t* in_ptr; const int32_t* in_src;
+    const int32_t* out_ptr; const int32_t* out_dst; const int32_t* out_slot;
+    int64_t N; int32_t H; int32_t F;
+    const float* Y; int64_t ldy; int64_t res_off; int64_t el_off; int64_t er_off;
+    int32_t res_mode; int32_t act; float negative_slope; int32_t mean_heads;
+    const float* bias; float attn_drop_p; uint32_t reserved0; uint64_t attn_seed;
+    float* att;
+    float* out; int64_t ldo; int32_t n_sinks; int32_t reserved1; spgnn_sink sinks[2];
+    int32_t n_gsrc; int32_t reserved2; spgnn_gsrc gsrc[3];
+    uint16_t* dY_hi; int64_t dY_ld; int64_t dY_ps;
+    float* g_ws; float* ds_ws; float* dbias; float* dbias_ws;
+} spgnn_gat_layer;
+int64_t spgnn_gat_layer_sizeof(void);
+int64_t spgnn_gat_layer_dbias_ws(int64_t N, int64_t H, int64_t F);
+int spgnn_gat_layer_fwd(const spgnn_gat_layer* L, void* stream);
+int spgnn_gat_layer_bwd(const spgnn_gat_layer* L, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Weighted-sum aggregation (DGL SpMM copy_u.sum with degree norms): GraphConv and GINConv-mean.

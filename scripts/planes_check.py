@@ -16,7 +16,7 @@ def to_planes(x, x2=None, p=0.0, seed=0):
     K2 = x2.shape[1] if x2 is not None else 0
     ld = (K1 + K2 + 63) // 64 * 64
     buf = torch.zeros(2, M, ld, dtype=torch.bfloat16, device=x.device)
-    L.split_planes(ptr(x), x.stride(0), K1, ptr(x2), x2.stride(0) if x2 is not None else 0, K2, p, seed, ptr(buf), ld,
+    L.split_planes(ptr(x), x.stride(0), K1, ptr(x2), x2.stride(0) if x2 is not None else 0, K2, p, seed, 0, 0, ptr(buf), ld,
                    M * ld, M, stream())
     return buf
 

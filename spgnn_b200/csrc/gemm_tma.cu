@@ -401,7 +401,8 @@ __device__ __forceinline__ uint64_t chunk_hash(uint64_t seed, uint64_t idx) { re
 // Mask: 16 hash bits per element, chunk index = row * nchunks + chunk (the convention of every plane producer).
 __global__ void split_planes_kernel(const float* __restrict__ x1, int64_t ld1, int K1, const float* __restrict__ x2,
                                     int64_t ld2, int K2, uint32_t thr, float scale, uint64_t seed,
-                                    __nv_bfloat16* __restrict__ hi, int64_t ldo, int64_t ps, int64_t M) {
+                                    int64_t cat_chunks, int64_t chunk_off, __nv_bfloat16* __restrict__ hi, int64_t ldo,
+                                    int64_t ps, int64_t M) {
     const int K = K1 + K2;
     const int nch = (K + 3) >> 2;
     const int64_t total = M * nch;
@@ -425,7 +426,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x1, int64_t ld1, i
             }
         }
         if (thr) {
-            const uint64_t h = chunk_hash(seed, (uint64_t)i);
+            const uint64_t h = chunk_hash(seed, (uint64_t)r * (uint64_t)cat_chunks + (uint64_t)(chunk_off + (c >> 2)));
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = ((uint32_t)(h >> (16 * j)) & 0xFFFFu) >= thr ? v[j] * scale : 0.f;
         }
@@ -556,8 +557,8 @@ void reduce_splits(const float* ws, int64_t splits, int64_t N, int64_t K, float*
 }
 
 extern "C" int spgnn_split_planes(const float* x1, int64_t ld1, int64_t K1, const float* x2, int64_t ld2, int64_t K2,
-                                  float p, uint64_t seed, uint16_t* out_hi, int64_t ldo, int64_t plane_stride,
-                                  int64_t M, void* stream) {
+                                  float p, uint64_t seed, int64_t concat_chunks, int64_t chunk_off, uint16_t* out_hi,
+                                  int64_t ldo, int64_t plane_stride, int64_t M, void* stream) {
     SPGNN_REQUIRE(x1 && out_hi && M > 0 && K1 > 0 && K2 >= 0 && (K2 == 0 || x2), "split_planes: bad argument");
     SPGNN_REQUIRE(ldo % 4 == 0 && ldo >= ((K1 + K2 + 3) / 4) * 4 && plane_stride % 4 == 0 && ((uintptr_t)out_hi & 7) == 0,
                   "split_planes: output ld (%lld) must be a multiple of 4 covering the padded row", (long long)ldo);
@@ -565,8 +566,9 @@ extern "C" int spgnn_split_planes(const float* x1, int64_t ld1, int64_t K1, cons
     const uint32_t thr = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     const int64_t total = M * ((K1 + K2 + 3) / 4);
+    if (concat_chunks <= 0) { concat_chunks = (K1 + K2 + 3) / 4; chunk_off = 0; }
     split_planes_kernel<<<split_grid(total), 256, 0, as_stream(stream)>>>(
-        x1, ld1, (int)K1, K2 > 0 ? x2 : nullptr, ld2, (int)K2, thr, scale, seed,
+        x1, ld1, (int)K1, K2 > 0 ? x2 : nullptr, ld2, (int)K2, thr, scale, seed, concat_chunks, chunk_off,
         reinterpret_cast<__nv_bfloat16*>(out_hi), ldo, plane_stride, M);
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;

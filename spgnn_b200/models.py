@@ -19,8 +19,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import nn as snn, ops
+from . import nn as snn, ops, stack
 from ._lib import SpgnnError
+
+# True: GAT-family stacks run through the planes pipeline (stack.py: TMA-fed tcgen05 projections over split-bf16
+# activations, layer kernels that write the next projection's operands).  False: one kernel family per op (ops.py).
+USE_STACK = True
 
 
 def set_trainable(model, trainable):
@@ -47,6 +51,26 @@ def _feats(g, h, key="fvs"):
 
 class _ConvStack(nn.Module):
     _resettable = (snn.GATConv, snn.GraphConv, snn.SAGEConv)
+
+    def _stack_plan(self):
+        """StackPlan of this module's GATConv wiring, or None when the planes pipeline does not cover it."""
+        plan = self.__dict__.get("_plan_cache")
+        if plan is None:
+            plan = self._build_plan()
+            self.__dict__["_plan_cache"] = plan if plan.supported() else False
+            plan = self.__dict__["_plan_cache"]
+        return plan or None
+
+    def _run_stack(self, g, ext, head):
+        """(logits or None, outputs) through the planes pipeline, or None when it does not apply."""
+        if not USE_STACK or any(t.requires_grad or not t.is_cuda for t in ext.values()):
+            return None
+        plan = self._stack_plan()
+        if plan is None:
+            return None
+        if any(not L.conv._allow_zero_in_degree for L in plan.layers):
+            g.check_no_zero_in_degree()
+        return stack.run_stack(plan, g, ext, self.training, head)
 
     def reset_parameters(self):
         for m in self.modules():
@@ -84,12 +108,23 @@ class GAT(_ConvStack):
             width = num_hiddens[i] * heads[i]
         self.gat_layers.append(snn.GATConv(width, out_ch, heads[num_layers], 0.0, 0.0, negative_slope, residual, None))
 
-    def forward(self, g, h=None):
+    def _build_plan(self):
+        n = len(self.gat_layers)
+        names = ["fvs"] + [f"h{i + 1}" for i in range(n - 1)] + ["emb"]
+        layers = [stack.LayerPlan(conv, [names[i]], names[i + 1], mean_heads=(i == n - 1))
+                  for i, conv in enumerate(self.gat_layers)]
+        return stack.StackPlan(layers, {"fvs": self.gat_layers[0]._in_feats}, ["emb"])
+
+    def forward(self, g, h=None, _head=None):
         h = _feats(g, h)
+        res = None if self.norm else self._run_stack(g, {"fvs": h}, _head)
+        if res is not None:
+            return (res[0], res[1][0]) if _head is not None else res[1][0]
         for conv in self.gat_layers[:-1]:
             h = conv.forward_flat(g, h)
         h = self.gat_layers[-1].forward_flat(g, h, mean_heads=True)
-        return F.normalize(h, p=2, dim=1) if self.norm else h
+        h = F.normalize(h, p=2, dim=1) if self.norm else h
+        return (_head(h), h) if _head is not None else h
 
 
 class GIN(nn.Module):
@@ -155,13 +190,29 @@ class GATPSPGNN(_ConvStack):
         self.gat_layers.append(snn.GATConv(s_w + p_w, out_ch, heads[num_layers], 0.0, 0.0, negative_slope, residual,
                                            activation))
 
-    def forward(self, g, h=None, p=None):
+    def _build_plan(self):
+        n = self.num_layers
+        s_names = ["fvs"] + [f"s{i + 1}" for i in range(n)]
+        p_names = ["pos_enc"] + [f"p{i + 1}" for i in range(n)]
+        layers = []
+        for i in range(n):
+            layers.append(stack.LayerPlan(self.gat_layers[i], [s_names[i], p_names[i]], s_names[i + 1]))
+            layers.append(stack.LayerPlan(self.pgnn_layers[i], [p_names[i]], p_names[i + 1]))
+        layers.append(stack.LayerPlan(self.gat_layers[n], [s_names[n], p_names[n]], "emb", mean_heads=True))
+        ext = {"fvs": self.gat_layers[0]._in_feats - self.pgnn_layers[0]._in_feats,
+               "pos_enc": self.pgnn_layers[0]._in_feats}
+        return stack.StackPlan(layers, ext, ["emb", p_names[n]])
+
+    def forward(self, g, h=None, p=None, _head=None):
         h_p, h_s = _feats(g, p, "pos_enc"), _feats(g, h)
+        res = self._run_stack(g, {"fvs": h_s, "pos_enc": h_p}, _head)
+        if res is not None:
+            return (res[0], res[1][0], res[1][1]) if _head is not None else (res[1][0], res[1][1])
         for s_conv, p_conv in zip(self.gat_layers[:-1], self.pgnn_layers):
             h_s = s_conv.forward_flat(g, h_s, h_p)     # consumes h_p BEFORE the position layer updates it
             h_p = p_conv.forward_flat(g, h_p)
         h_s = self.gat_layers[-1].forward_flat(g, h_s, h_p, mean_heads=True)
-        return h_s, h_p
+        return (_head(h_s), h_s, h_p) if _head is not None else (h_s, h_p)
 
 
 class GATPSPGNNNL(_ConvStack):
@@ -181,11 +232,23 @@ class GATPSPGNNNL(_ConvStack):
         self.gat_layers.append(snn.GATConv(s_w + pos_in_dim, out_ch, heads[num_layers], 0.0, 0.0, negative_slope,
                                            residual, activation))
 
-    def forward(self, g, h=None, p=None):
+    def _build_plan(self):
+        n = len(self.gat_layers)
+        names = ["fvs"] + [f"s{i + 1}" for i in range(n - 1)] + ["emb"]
+        layers = [stack.LayerPlan(conv, [names[i], "pos_enc"], names[i + 1], mean_heads=(i == n - 1))
+                  for i, conv in enumerate(self.gat_layers)]
+        pw = self.gat_layers[1]._in_feats - self.gat_layers[0]._out_feats * self.gat_layers[0]._num_heads
+        return stack.StackPlan(layers, {"fvs": self.gat_layers[0]._in_feats - pw, "pos_enc": pw}, ["emb"])
+
+    def forward(self, g, h=None, p=None, _head=None):
         h_p, h_s = _feats(g, p, "pos_enc"), _feats(g, h)
+        res = self._run_stack(g, {"fvs": h_s, "pos_enc": h_p}, _head)
+        if res is not None:
+            return (res[0], res[1][0], h_p) if _head is not None else (res[1][0], h_p)
         for conv in self.gat_layers[:-1]:
             h_s = conv.forward_flat(g, h_s, h_p)
-        return self.gat_layers[-1].forward_flat(g, h_s, h_p, mean_heads=True), h_p
+        h_s = self.gat_layers[-1].forward_flat(g, h_s, h_p, mean_heads=True)
+        return (_head(h_s), h_s, h_p) if _head is not None else (h_s, h_p)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -288,6 +351,9 @@ class GATNet(_GNNNet):
                        negative_slope=negative_slope, residual=res)
         self._finish(node_embed_dim, out_ch)
 
+    def forward(self, g, h=None):
+        return self.gat(g, h, _head=self.gnn_out)        # (n_out, n_embed); the head shares the stack's planes
+
 
 class GINNet(_GNNNet):
     _gnn_attr = "gin"
@@ -348,8 +414,7 @@ class GATPositionSPGNNNet(_GNNNet):
         self._finish(node_embed_dim, out_ch)
 
     def forward(self, g, h=None, p=None):
-        n_embed, n_p_embed = self.gat(g, h, p)
-        return self.gnn_out(n_embed), n_embed, n_p_embed
+        return self.gat(g, h, p, _head=self.gnn_out)     # (n_out, n_embed, n_p_embed)
 
     def forward_emb(self, g, h=None, p=None):
         return self.gat(g, h, p)
