@@ -97,15 +97,12 @@ class HostBatch:
         return sum(t.numel() * t.element_size() for t in (self.n_nodes, self.adj_cat, self.fvs, self.fvs_out, self.labels))
 
 
-def batch_to_device(hb: HostBatch, pos_enc_dim=39, device=None, pe_kind="dist"):
-    """Host buffers → device graph batch with features and positional encoding: the per-batch part of
-    GCNTrainSPGNN.train (job_runner.py:1872-1882) — H2D copies, from_adj_to_graph for every scan, PE, dgl.batch."""
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-    n_nodes = hb.n_nodes.to(dev, non_blocking=True)
-    adj = hb.adj_cat.to(dev, non_blocking=True)
-    fvs = hb.fvs.to(dev, non_blocking=True)
-    fvs_out = hb.fvs_out.to(dev, non_blocking=True)
-    labels = hb.labels.to(dev, non_blocking=True)
+def _upload(hb: HostBatch, dev):
+    return tuple(t.to(dev, non_blocking=True) for t in (hb.n_nodes, hb.adj_cat, hb.fvs, hb.fvs_out, hb.labels))
+
+
+def _assemble(hb: HostBatch, bufs, dev, pos_enc_dim, pe_kind):
+    n_nodes, adj, fvs, fvs_out, labels = bufs
     n_edges, sl, dl = sg._edges_from_dense(adj, n_nodes, dev)
     g = sg.Graph.from_edge_lists(n_nodes, n_edges, sl, dl, max_nodes=hb.max_nodes, check=False)
     g.ndata["fvs"], g.ndata["fvs_out"], g.ndata["y"] = fvs, fvs_out, labels
@@ -115,6 +112,55 @@ def batch_to_device(hb: HostBatch, pos_enc_dim=39, device=None, pe_kind="dist"):
         else:
             g.ndata["pos_enc"] = spe.rw_pos_enc(g, pos_enc_dim)
     return g
+
+
+def batch_to_device(hb: HostBatch, pos_enc_dim=39, device=None, pe_kind="dist"):
+    """Host buffers → device graph batch with features and positional encoding: the per-batch part of
+    GCNTrainSPGNN.train (job_runner.py:1872-1882) — H2D copies, from_adj_to_graph for every scan, PE, dgl.batch."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    return _assemble(hb, _upload(hb, dev), dev, pos_enc_dim, pe_kind)
+
+
+class DeviceBatchLoader:
+    """Iterates device batches over an iterable of :class:`HostBatch`, with the H2D copy of batch i+1 running on
+    a copy stream while the caller computes on batch i (the reference copies synchronously inside the loop,
+    job_runner.py:1872-1875).  Every batch is copied from (pinned) host memory each time it is yielded; graph
+    build and positional encoding run on the caller's stream once that batch's copy has landed."""
+
+    def __init__(self, host_batches, pos_enc_dim=39, device=None, pe_kind="dist"):
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.it = iter(host_batches)
+        self.pos_enc_dim, self.pe_kind = pos_enc_dim, pe_kind
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self._pending = None
+        self._issue()
+
+    def _issue(self):
+        try:
+            hb = next(self.it)
+        except StopIteration:
+            self._pending = None
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        # destination blocks come from the copy stream's pool; record_stream hands them to the caller's stream
+        with torch.cuda.stream(self.copy_stream):
+            bufs = _upload(hb, self.dev)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        for t in bufs:
+            t.record_stream(cur)
+        self._pending = (hb, bufs, done)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._pending is None:
+            raise StopIteration
+        hb, bufs, done = self._pending
+        torch.cuda.current_stream(self.dev).wait_event(done)
+        self._issue()                      # next batch's copy overlaps this batch's graph build + step
+        return _assemble(hb, bufs, self.dev, self.pos_enc_dim, self.pe_kind)
 
 
 def host_batch_from_graph(g, pin=True):
