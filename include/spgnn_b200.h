@@ -242,6 +242,60 @@ int spgnn_gat_layer_fwd(const spgnn_gat_layer* L, void* stream);
 int spgnn_gat_layer_bwd(const spgnn_gat_layer* L, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Aggregate-first evaluation of the head-averaged GAT OUTPUT layer (models.py:311-314 / :436-440 followed by
+ * `.mean(1)`, models.py:326,482): `GATConv(k_in -> H x F, residual)` with H*F >> k_in (192 -> 2 x 1024 in SPGNN-3).
+ * Aggregation is linear, so  sum_u a[u->v,h] (x[u] W_h^T) = (sum_u a[u->v,h] x[u]) W_h^T : the edge softmax and
+ * the neighbour aggregation run on the NARROW input (k_in columns) and one tcgen05 GEMM per (row tile, head)
+ *     pre_h = [Ax_h | x] * [W_fc,h | W_res,h]^T + b_h ,   out = 1/H sum_h act(pre_h)
+ * applies activation and head mean in its epilogue: the [N, 2*H*F] projection (20 GB at 4096 trees) is never
+ * written to HBM.  The backward RECOMPUTES pre_h with the same kernel (mode 1) and emits
+ * dpre_h = g/H * act'(pre_h) as planes, plus the bias gradient; dW / d[Ax|x] are ordinary planes GEMMs on dpre.
+ *   eler  fp32 [N, 2H]: el[h] at column h, er[h] at column H+h (a [2H, k_in] projection of the same input).
+ *   XA    planes [N, (H+1)*kp], kp = k_in rounded up to 64: block h < H = Ax_h, block H = x (a copy of the
+ *         concatenated, already feat-dropped input); padding columns are written as zeros.  K1 % 64 == 0.
+ *   aggx_fwd : att [E,H] and XA from (X1 | X2, eler).
+ *   aggx_bwd : from dXA fp32 [H][N, ld_dxa] (cols [0,k4) = d(Ax_h), [k4, 2*k4) = d(x) through the residual;
+ *              k4 = k_in rounded up to 4; the second half is read only when has_res) computes the edge-softmax
+ *              backward on the narrow rows, d_eler (fp32 + planes, for the dW of the logit projection) and
+ *              dX fp32 [N, k_in] = d(concatenated input), including the logit path d_eler * w_eler.
+ * ---------------------------------------------------------------------------------- */
+typedef struct spgnn_gat_wide {
+    const int32_t* in_ptr; const int32_t* in_src;
+    const int32_t* out_ptr; const int32_t* out_dst; const int32_t* out_slot;
+    int64_t N; int32_t H; int32_t has_res;
+    const uint16_t* X1; int64_t ldx1; int64_t psx1;
+    const uint16_t* X2; int64_t ldx2; int64_t psx2;
+    int32_t K1; int32_t K2;
+    const float* eler; int64_t ld_eler;
+    float negative_slope; float attn_drop_p; uint64_t attn_seed;
+    float* att;
+    uint16_t* XA; int64_t ldxa; int64_t psxa; int64_t kp;
+    const float* dXA; int64_t ld_dxa; int64_t head_stride;
+    const float* w_eler; int64_t ld_w;
+    float* ds_ws;
+    float* d_eler; int64_t ld_de;
+    uint16_t* d_eler_planes; int64_t ld_dep; int64_t ps_dep;
+    float* dX; int64_t ld_dx;
+} spgnn_gat_wide;
+int64_t spgnn_gat_wide_sizeof(void);
+int spgnn_gat_aggx_fwd(const spgnn_gat_wide* L, void* stream);
+int spgnn_gat_aggx_bwd(const spgnn_gat_wide* L, void* stream);
+
+/* The wide GEMM.  W: fp32 packed weight [>= (1+has_res)*H*F rows, ldw]: rows [0,HF) = W_fc, [HF,2HF) = W_res,
+ * k_in valid columns each.  bias [H*F] or NULL.
+ *   mode 0: out fp32 [N, ldo] (optional) and/or out planes (optional) <- 1/H sum_h act(pre_h)      (width F)
+ *   mode 1: g = sum of n_g fp32 [N, F] gradient sources; dpre planes [N, H*F] <- g/H * act'(pre_h);
+ *           dbias [H*F] (optional) <- column sums of dpre (per-CTA partial rows reduced in fixed order).
+ * ws: spgnn_wide_linear_ws bytes. */
+int64_t spgnn_wide_linear_ws(int64_t H, int64_t F, int64_t kp, int has_res);
+int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa, int64_t kp, int64_t k_in, int64_t M,
+                      int H, int F, int has_res, const float* W, int64_t ldw, const float* bias, int act, int mode,
+                      float* out, int64_t ldo, uint16_t* out_planes, int64_t ldp, int64_t psp,
+                      const float* g0, int64_t ldg0, const float* g1, int64_t ldg1, const float* g2, int64_t ldg2,
+                      uint16_t* dpre, int64_t ldd, int64_t psd, float* dbias,
+                      void* ws, int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Weighted-sum aggregation (DGL SpMM copy_u.sum with degree norms): GraphConv and GINConv-mean.
  *   out[v, :] = act( post[v] * sum_{s in seg(v)} pre[nbr[s]] * x[nbr[s], :] + self_coef * x[v, :] + bias )
  * pre/post/bias may be null; self_coef is read from device memory (GIN's 1+eps) when self_coef_ptr != null

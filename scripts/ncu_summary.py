@@ -22,10 +22,24 @@ for vals in rows[2:]:
             print(f"  {k:80s} {d[k]:>16s} {u[k]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-h = rows[1]
-i_src, i_s, i_ex = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
-data = [(int(r[i_s] or 0), r[i_src].strip(), int(r[i_ex] or 0), n) for n, r in enumerate(rows[2:]) if len(r) > i_s]
-tot = sum(x[0] for x in data) or 1
-print(f"  -- {len(data)} SASS instructions, {tot} samples; top by stall samples:")
-for s_, src_, ex, n in sorted(data, key=lambda x: -x[0])[:topn]:
-    print(f"  {100*s_/tot:5.1f}%  ex={ex:10d} #{n:5d} {src_[:100]}")
+# one block per kernel: a title row, a header row ("Source", "# Samples", ...), then one row per SASS instruction
+blocks, cur = [], None
+for r in rows:
+    if "Source" in r and "# Samples" in r:
+        cur = {"h": r, "rows": []}
+        blocks.append(cur)
+    elif cur is not None and len(r) == len(cur["h"]):
+        cur["rows"].append(r)
+for bi, b in enumerate(blocks):
+    h = b["h"]
+    i_src, i_s, i_ex = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
+    data = []
+    for n, r in enumerate(b["rows"]):
+        try:
+            data.append((int(r[i_s] or 0), r[i_src].strip(), int(r[i_ex] or 0), n))
+        except ValueError:
+            pass
+    tot = sum(x[0] for x in data) or 1
+    print(f"  -- kernel #{bi}: {len(data)} SASS instructions, {tot} samples; top by stall samples:")
+    for s_, src_, ex, n in sorted(data, key=lambda x: -x[0])[:topn]:
+        print(f"  {100*s_/tot:5.1f}%  ex={ex:10d} #{n:5d} {src_[:100]}")

@@ -225,6 +225,288 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
     }
 }
 
+// ---------------------------------------------------------------------------------------------- wide (output layer)
+// out = 1/H sum_h act([Ax_h | x] * [W_fc,h | W_res,h]^T + b_h)   (spgnn_wide_linear, include/spgnn_b200.h)
+// A = XA planes [M, (H+1)*kp] (block h = Ax_h, block H = x), B = weight planes [H*F, nparts*kp].  A tile is 128 rows x
+// BN columns x H heads: H accumulators of BN TMEM columns each (x 2 buffers), the k-loop runs head after head; the
+// epilogue walks the heads one at a time, so per thread only the running mean (mode 0) or the incoming gradient
+// (mode 1) stays in registers.
+struct WideMaps { CUtensorMap a, b; };
+struct WideArgs {
+    int mode, H, F, act;
+    const float* bias;
+    float* out; int64_t ldo;
+    __nv_bfloat16* outp; int64_t ldp, psp;
+    const float* g[3]; int64_t ldg[3]; int n_g;
+    __nv_bfloat16* dpre; int64_t ldd, psd;
+    float* dbias_ws;
+    int64_t M; int BN, nt_n; int64_t nt_m;
+    int kbp, nparts, kp;
+    int stages, stage_bytes;
+};
+constexpr int kWideEpiWarps = 8;                       // two warps per TMEM lane quadrant, alternating column chunks
+constexpr int kWideThreads = (kWideEpiWarps + 2) * 32;
+constexpr int kWideStgBytes = kWideEpiWarps * 32 * 16 * 4;   // one swizzled 32 x 16 fp32 tile per epilogue warp
+constexpr int kWideFixed = 1024 /*align*/ + 256 /*barriers*/ + kWideStgBytes;
+
+template <int ACT>
+__device__ __forceinline__ float wide_act(float x, int act) {
+    if (ACT == SPGNN_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+    if (ACT == SPGNN_ACT_NONE) return x;
+    return act_fwd(x, act, 0.f);
+}
+template <int ACT>
+__device__ __forceinline__ float wide_act_grad(float y, int act) {
+    if (ACT == SPGNN_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+    if (ACT == SPGNN_ACT_NONE) return 1.f;
+    return act_grad_from_out(y, act, 0.f);
+}
+__device__ __forceinline__ void st_planes4(__nv_bfloat16* q, int64_t ps, float4 d) {
+    uint32_t h0, l0, h1, l1;
+    split2(d.x, d.y, h0, l0);
+    split2(d.z, d.w, h1, l1);
+    *reinterpret_cast<uint2*>(q) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(q + ps) = make_uint2(l0, l1);
+}
+
+// Epilogue of one 128 x BN x H tile for one warp: 16-column chunks; TMEM (lane = row) -> swizzled smem tile ->
+// (row = lane/4 + 8i, 4 columns) per thread, so that global accesses are whole 32/64-byte row segments.  In mode 1
+// the incoming gradient of the warp's four chunks is loaded BEFORE waiting for the accumulator, so its DRAM latency
+// hides behind the MMAs of this tile.
+template <int ACT>
+__device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg, float* sb, uint32_t taddr, int64_t m0,
+                                                   int n0, int ncols, int warp, int lane, uint32_t full_bar,
+                                                   uint32_t full_par) {
+    const int quad = warp & 3, half = warp >> 2;
+    const int r0 = lane >> 2, cq = lane & 3;
+    const float inv_h = 1.f / (float)g.H;
+    const int64_t row0 = m0 + quad * 32 + r0;
+    const int nrow = (int)max((int64_t)0, min((int64_t)4, (g.M - row0 + 7) / 8));
+    for (int cg = 0; cg < ncols; cg += 128) {
+        float4 run[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c0 = cg + q * 32 + half * 16;
+            const int col = n0 + c0 + cq * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                run[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.mode == 1 && i < nrow && c0 < ncols) {
+                    const int64_t r = row0 + 8 * i;
+                    for (int s = 0; s < g.n_g; ++s) {
+                        const float4 t = ldg4(g.g[s] + r * g.ldg[s] + col);
+                        run[q][i].x += t.x; run[q][i].y += t.y; run[q][i].z += t.z; run[q][i].w += t.w;
+                    }
+                    run[q][i].x *= inv_h; run[q][i].y *= inv_h; run[q][i].z *= inv_h; run[q][i].w *= inv_h;
+                }
+            }
+        }
+        if (cg == 0) {
+            mbar_wait(full_bar, full_par);
+            tc_fence_after();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c0 = cg + q * 32 + half * 16;
+            if (c0 >= ncols) break;
+            const int col = n0 + c0 + cq * 4;
+            for (int h = 0; h < g.H; ++h) {
+                uint32_t v[16];
+                tmem_ld16(taddr + h * g.BN + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+                const float4 bv = g.bias ? ldg4(g.bias + h * g.F + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + 8 * i;
+                    float4 x = *reinterpret_cast<const float4*>(stg + r * 16 + ((cq ^ ((r >> 1) & 3)) << 2));
+                    x.x = wide_act<ACT>(x.x + bv.x, g.act);
+                    x.y = wide_act<ACT>(x.y + bv.y, g.act);
+                    x.z = wide_act<ACT>(x.z + bv.z, g.act);
+                    x.w = wide_act<ACT>(x.w + bv.w, g.act);
+                    if (g.mode == 0) {
+                        run[q][i].x += x.x; run[q][i].y += x.y; run[q][i].z += x.z; run[q][i].w += x.w;
+                    } else if (i < nrow) {
+                        float4 d;
+                        d.x = run[q][i].x * wide_act_grad<ACT>(x.x, g.act);
+                        d.y = run[q][i].y * wide_act_grad<ACT>(x.y, g.act);
+                        d.z = run[q][i].z * wide_act_grad<ACT>(x.z, g.act);
+                        d.w = run[q][i].w * wide_act_grad<ACT>(x.w, g.act);
+                        st_planes4(g.dpre + (row0 + 8 * i) * g.ldd + h * g.F + col, g.psd, d);
+                        bs.x += d.x; bs.y += d.y; bs.z += d.z; bs.w += d.w;
+                    }
+                }
+                if (g.mode == 1 && g.dbias_ws) {
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        bs.x += __shfl_xor_sync(kFull, bs.x, o); bs.y += __shfl_xor_sync(kFull, bs.y, o);
+                        bs.z += __shfl_xor_sync(kFull, bs.z, o); bs.w += __shfl_xor_sync(kFull, bs.w, o);
+                    }
+                    if (lane < 4) {
+                        float* p = sb + h * g.F + col;
+                        atomicAdd(p, bs.x); atomicAdd(p + 1, bs.y); atomicAdd(p + 2, bs.z); atomicAdd(p + 3, bs.w);
+                    }
+                }
+                __syncwarp();
+            }
+            if (g.mode == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < nrow) {
+                        const int64_t r = row0 + 8 * i;
+                        const float4 y = make_float4(run[q][i].x * inv_h, run[q][i].y * inv_h, run[q][i].z * inv_h,
+                                                     run[q][i].w * inv_h);
+                        if (g.out) st4(g.out + r * g.ldo + col, y);
+                        if (g.outp) st_planes4(g.outp + r * g.ldp + col, g.psp, y);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_constant__ WideMaps maps, const WideArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stages_bytes = g.stages * g.stage_bytes;
+    NtShared* sh = reinterpret_cast<NtShared*>(smem + stages_bytes);
+    float* sb = reinterpret_cast<float*>(smem + stages_bytes + 256 + kWideStgBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const int HF = g.H * g.F;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(smem_u32(&sh->full[s]), 1);
+            mbar_init(smem_u32(&sh->empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&sh->tmem_full[b]), 1);
+            mbar_init(smem_u32(&sh->tmem_empty[b]), kWideEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (g.dbias_ws)
+        for (int i = threadIdx.x; i < HF; i += kWideThreads) sb[i] = 0.f;
+    if (warp == kWideEpiWarps + 1 && lane == 0) {
+        prefetch_tmap(&maps.a);
+        prefetch_tmap(&maps.b);
+    }
+    if (warp == kWideEpiWarps) tmem_alloc(smem_u32(&sh->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    const int64_t n_tiles = g.nt_m * g.nt_n;
+    const int nkb = g.nparts * g.kbp;                // k-blocks per head
+    const int accw = g.H * g.BN;                     // TMEM columns per accumulator buffer
+
+    if (warp < kWideEpiWarps) {
+        // ===================================================== epilogue
+        int it = 0;
+        float* stg = reinterpret_cast<float*>(smem + stages_bytes + 256) + warp * (32 * 16);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t par = (it >> 1) & 1;
+            const int64_t m0 = (tile / g.nt_n) * BM;
+            const int n0 = (int)(tile % g.nt_n) * g.BN;
+            const int ncols = min(g.BN, g.F - n0);
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * accw);
+            const uint32_t fb = smem_u32(&sh->tmem_full[buf]);
+            if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU>(g, stg, sb, taddr, m0, n0, ncols, warp, lane, fb, par);
+            else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE>(g, stg, sb, taddr, m0, n0, ncols, warp, lane, fb, par);
+            else wide_epilogue_tile<-1>(g, stg, sb, taddr, m0, n0, ncols, warp, lane, fb, par);
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sh->tmem_empty[buf]));
+        }
+    } else if (warp == kWideEpiWarps) {
+        // ===================================================== UMMA issuer
+        if (lane == 0) {
+            int it = 0;
+            uint32_t kcount = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t par = (it >> 1) & 1;
+                const int n0 = (int)(tile % g.nt_n) * g.BN;
+                const int ncols = min(g.BN, g.F - n0);
+                const uint32_t idesc = make_idesc(ncols, false);
+                mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);
+                tc_fence_after();
+                for (int h = 0; h < g.H; ++h) {
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * accw + h * g.BN);
+                    for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                        const int s = kcount % g.stages;
+                        const uint32_t sp = (kcount / g.stages) & 1;
+                        mbar_wait(smem_u32(&sh->full[s]), sp);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_base + s * g.stage_bytes;
+                        const uint32_t a_lo = a_hi + BM * 128;
+                        const uint32_t b_hi = a_hi + kABytes;
+                        const uint32_t b_lo = b_hi + g.BN * 128;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t ko = k * 32;
+                            const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                            const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                            umma_bf16(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                            umma_bf16(tmem_d, dah, dbl, idesc, 1);
+                            umma_bf16(tmem_d, dal, dbh, idesc, 1);
+                        }
+                        umma_commit(smem_u32(&sh->empty[s]));
+                    }
+                }
+                umma_commit(smem_u32(&sh->tmem_full[buf]));
+            }
+        }
+    } else if (lane == 0) {
+        // ===================================================== TMA producer
+        uint32_t kcount = 0;
+        const uint32_t tx = (uint32_t)g.stage_bytes;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m0 = (int)((tile / g.nt_n) * BM);
+            const int n0 = (int)(tile % g.nt_n) * g.BN;
+            for (int h = 0; h < g.H; ++h) {
+                for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                    const int s = kcount % g.stages;
+                    const uint32_t sp = (kcount / g.stages) & 1;
+                    mbar_wait(smem_u32(&sh->empty[s]), sp ^ 1);
+                    const uint32_t bar = smem_u32(&sh->full[s]);
+                    mbar_expect_tx(bar, tx);
+                    const uint32_t dst = smem_base + s * g.stage_bytes;
+                    const int part = kb / g.kbp, j = kb - part * g.kbp;
+                    const int acol = (part == 0 ? h : g.H) * g.kp + j * BK;
+                    tma_load_3d(dst, &maps.a, bar, acol, m0, 0);
+                    tma_load_3d(dst + kABytes, &maps.b, bar, kb * BK, h * g.F + n0, 0);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (g.dbias_ws)
+        for (int i = threadIdx.x; i < HF; i += kWideThreads) g.dbias_ws[(int64_t)blockIdx.x * HF + i] = sb[i];
+    if (warp == kWideEpiWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void wide_dbias_reduce_kernel(const float* __restrict__ part, int64_t nparts, int64_t HF, float* __restrict__ out) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < HF; c += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int64_t p = 0; p < nparts; ++p) s += part[p * HF + c];
+        out[c] = s;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- TN kernel (dW)
 constexpr int T_BK = 32;                       // nodes per stage
 constexpr int T_BLK = 2 * T_BK * 128;          // one 64-column block, hi + lo planes: 8 KB
@@ -598,6 +880,93 @@ extern "C" int spgnn_planes_linear_fwd(const uint16_t* A1, int64_t lda1, int64_t
     return launch_nt(reinterpret_cast<const __nv_bfloat16*>(A1), lda1, ps1, K1,
                      reinterpret_cast<const __nv_bfloat16*>(A2), lda2, ps2, K2, hi, ldb, bias, act, slope, C, ldc, M, N,
                      st);
+}
+
+extern "C" int64_t spgnn_wide_linear_ws(int64_t H, int64_t F, int64_t kp, int has_res) {
+    const int64_t b = 2 * H * F * (has_res ? 2 : 1) * kp * (int64_t)sizeof(__nv_bfloat16);
+    return b + 256 + (int64_t)sm_count() * H * F * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa, int64_t kp, int64_t k_in, int64_t M,
+                                 int H, int F, int has_res, const float* W, int64_t ldw, const float* bias, int act,
+                                 int mode, float* out, int64_t ldo, uint16_t* out_planes, int64_t ldp, int64_t psp,
+                                 const float* g0, int64_t ldg0, const float* g1, int64_t ldg1, const float* g2,
+                                 int64_t ldg2, uint16_t* dpre, int64_t ldd, int64_t psd, float* dbias, void* ws,
+                                 int64_t ws_bytes, void* stream) {
+    SPGNN_REQUIRE(XA && W && ws && M > 0 && k_in > 0, "wide_linear: bad argument");
+    SPGNN_REQUIRE(H == 1 || H == 2 || H == 4, "wide_linear: H must be 1, 2 or 4 (got %d)", H);
+    SPGNN_REQUIRE(F > 0 && F % 32 == 0 && (int64_t)H * F <= 4096, "wide_linear: F (%d) must be a multiple of 32, H*F <= 4096", F);
+    SPGNN_REQUIRE(kp % BK == 0 && kp >= k_in && ldxa >= (H + 1) * kp && ldw >= k_in, "wide_linear: kp / ld mismatch");
+    SPGNN_REQUIRE(mode == 0 || mode == 1, "wide_linear: mode must be 0 (forward) or 1 (gradient of the pre-activations)");
+    SPGNN_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "wide_linear: bias must be 16-byte aligned");
+    SPGNN_REQUIRE(ws_bytes >= spgnn_wide_linear_ws(H, F, kp, has_res), "wide_linear: workspace too small");
+    SPGNN_REQUIRE(M < (1ll << 31), "wide_linear: too many rows");
+    WideMaps maps;
+    WideArgs a{};
+    a.mode = mode; a.H = H; a.F = F; a.act = act; a.bias = bias; a.M = M;
+    if (mode == 0) {
+        SPGNN_REQUIRE(out || out_planes, "wide_linear: no output");
+        SPGNN_REQUIRE(!out || (ldo % 4 == 0 && ldo >= F && ((uintptr_t)out & 15) == 0), "wide_linear: out alignment");
+        SPGNN_REQUIRE(!out_planes || (ldp % 4 == 0 && ldp >= F && psp % 4 == 0 && ((uintptr_t)out_planes & 7) == 0),
+                      "wide_linear: out planes alignment");
+        a.out = out; a.ldo = ldo; a.outp = reinterpret_cast<__nv_bfloat16*>(out_planes); a.ldp = ldp; a.psp = psp;
+    } else {
+        SPGNN_REQUIRE(g0 && dpre, "wide_linear: mode 1 needs a gradient source and the dpre planes");
+        SPGNN_REQUIRE(ldd % 4 == 0 && ldd >= (int64_t)H * F && psd % 4 == 0 && ((uintptr_t)dpre & 7) == 0,
+                      "wide_linear: dpre planes alignment");
+        const float* gs[3] = {g0, g1, g2};
+        const int64_t lds[3] = {ldg0, ldg1, ldg2};
+        for (int s = 0; s < 3; ++s) {
+            if (!gs[s]) continue;
+            SPGNN_REQUIRE(lds[s] % 4 == 0 && lds[s] >= F && ((uintptr_t)gs[s] & 15) == 0,
+                          "wide_linear: gradient source %d must be 16-byte aligned with ld %% 4 == 0", s);
+            a.g[a.n_g] = gs[s]; a.ldg[a.n_g] = lds[s]; ++a.n_g;
+        }
+        a.dpre = reinterpret_cast<__nv_bfloat16*>(dpre); a.ldd = ldd; a.psd = psd;
+    }
+    cudaStream_t st = as_stream(stream);
+    static bool attr = false;
+    if (!attr) {
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr = true;
+    }
+    const int nparts = has_res ? 2 : 1;
+    const int64_t HF = (int64_t)H * F, ldb = nparts * kp;
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(((uintptr_t)ws + 127) & ~(uintptr_t)127);
+    for (int p = 0; p < nparts; ++p) {
+        split_weight_kernel<<<split_grid(HF * kp), 256, 0, st>>>(W + (int64_t)p * HF * ldw, ldw, 0, 0, (int)HF, (int)kp,
+                                                                 (int)k_in, (int)kp, 0, 0, hi + p * kp,
+                                                                 hi + HF * ldb + p * kp, ldb);
+        SPGNN_LAUNCH_OK();
+    }
+    a.BN = 256 / H;
+    if (a.BN > F) a.BN = F;
+    a.nt_n = (int)ceil_div(F, a.BN);
+    a.nt_m = ceil_div(M, BM);
+    a.kbp = (int)(kp / BK); a.nparts = nparts; a.kp = (int)kp;
+    int rc = make_planes_map(&maps.a, XA, M, (int64_t)(H + 1) * kp, ldxa, psxa, BK, BM);
+    if (rc) return rc;
+    rc = make_planes_map(&maps.b, hi, HF, ldb, ldb, HF * ldb, BK, a.BN);
+    if (rc) return rc;
+    a.stage_bytes = kABytes + a.BN * 256;
+    const int fixed = kWideFixed + (int)HF * 4;
+    a.stages = (kSmemLimit - fixed) / a.stage_bytes;
+    if (a.stages > kMaxStages) a.stages = kMaxStages;
+    SPGNN_REQUIRE(a.stages >= 2, "wide_linear: not enough shared memory for two pipeline stages");
+    const int64_t tiles = a.nt_m * a.nt_n;
+    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    float* part = nullptr;
+    if (mode == 1 && dbias) {
+        part = reinterpret_cast<float*>(((uintptr_t)(hi + 2 * HF * ldb) + 255) & ~(uintptr_t)255);
+        a.dbias_ws = part;
+    }
+    wide_kernel<<<grid, kWideThreads, kSmemLimit, st>>>(maps, a);
+    SPGNN_LAUNCH_OK();
+    if (part) {
+        wide_dbias_reduce_kernel<<<(unsigned)ceil_div(HF, 128), 128, 0, st>>>(part, grid, HF, dbias);
+        SPGNN_LAUNCH_OK();
+    }
+    return SPGNN_OK;
 }
 
 extern "C" int64_t spgnn_planes_linear_bwd_input_ws(int64_t N, int64_t K) {

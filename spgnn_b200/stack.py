@@ -55,6 +55,29 @@ class _Layer(ctypes.Structure):
                 ("dbias_ws", ctypes.c_void_p)]
 
 
+class _Wide(ctypes.Structure):
+    _fields_ = [("in_ptr", ctypes.c_void_p), ("in_src", ctypes.c_void_p), ("out_ptr", ctypes.c_void_p),
+                ("out_dst", ctypes.c_void_p), ("out_slot", ctypes.c_void_p),
+                ("N", ctypes.c_int64), ("H", ctypes.c_int32), ("has_res", ctypes.c_int32),
+                ("X1", ctypes.c_void_p), ("ldx1", ctypes.c_int64), ("psx1", ctypes.c_int64),
+                ("X2", ctypes.c_void_p), ("ldx2", ctypes.c_int64), ("psx2", ctypes.c_int64),
+                ("K1", ctypes.c_int32), ("K2", ctypes.c_int32),
+                ("eler", ctypes.c_void_p), ("ld_eler", ctypes.c_int64),
+                ("negative_slope", ctypes.c_float), ("attn_drop_p", ctypes.c_float), ("attn_seed", ctypes.c_uint64),
+                ("att", ctypes.c_void_p),
+                ("XA", ctypes.c_void_p), ("ldxa", ctypes.c_int64), ("psxa", ctypes.c_int64), ("kp", ctypes.c_int64),
+                ("dXA", ctypes.c_void_p), ("ld_dxa", ctypes.c_int64), ("head_stride", ctypes.c_int64),
+                ("w_eler", ctypes.c_void_p), ("ld_w", ctypes.c_int64),
+                ("ds_ws", ctypes.c_void_p),
+                ("d_eler", ctypes.c_void_p), ("ld_de", ctypes.c_int64),
+                ("d_eler_planes", ctypes.c_void_p), ("ld_dep", ctypes.c_int64), ("ps_dep", ctypes.c_int64),
+                ("dX", ctypes.c_void_p), ("ld_dx", ctypes.c_int64)]
+
+
+# Aggregate-first evaluation of head-averaged output layers (include/spgnn_b200.h, spgnn_gat_wide).  Switch off to
+# run every layer through the projection-first kernels (tests compare the two).
+WIDE_OUTPUT_LAYER = True
+
 _checked = False
 
 
@@ -64,6 +87,9 @@ def _check_abi():
         n = int(lib().gat_layer_sizeof())
         if n != ctypes.sizeof(_Layer):
             raise SpgnnError(f"spgnn_gat_layer layout mismatch: library {n} bytes, binding {ctypes.sizeof(_Layer)}")
+        n = int(lib().gat_wide_sizeof())
+        if n != ctypes.sizeof(_Wide):
+            raise SpgnnError(f"spgnn_gat_wide layout mismatch: library {n} bytes, binding {ctypes.sizeof(_Wide)}")
         _checked = True
 
 
@@ -86,6 +112,19 @@ class Planes:
 
     def float(self):
         return (self.buf[0].float() + self.buf[1].float())[:, :self.cols]
+
+
+class PlanesView:
+    """Columns [col0, col0 + cols) of a Planes (same rows, ld and plane stride)."""
+
+    __slots__ = ("buf", "rows", "cols", "ld", "ps", "_p")
+
+    def __init__(self, base, col0, cols):
+        self.buf, self.rows, self.cols, self.ld, self.ps = base.buf, base.rows, int(cols), base.ld, base.ps
+        self._p = base.ptr(int(col0))
+
+    def ptr(self, col=0):
+        return self._p + 2 * col
 
 
 def split_planes(x, p=0.0, seed=0, concat_chunks=0, chunk_off=0, x2=None):
@@ -124,11 +163,11 @@ def planes_linear(A1: Planes, W, bias=None, act=0, slope=0.0, A2: Planes | None 
     return C
 
 
-def planes_linear_bwd_input(dC: Planes, W, K, k_off=0):
+def planes_linear_bwd_input(dC: Planes, W, K, k_off=0, out=None):
     """fp32 [M, K] = dC @ W[:, k_off:k_off+K]"""
     W = ops._rows(W)
     M, N = dC.rows, dC.cols
-    dA = ops.empty_padded(M, K, W.device)
+    dA = ops.empty_padded(M, K, W.device) if out is None else out
     L = lib()
     ws = _ws(L.planes_linear_bwd_input_ws(N, K), W.device)
     L.planes_linear_bwd_input(dC.ptr(), dC.ld, dC.ps, ptr(W), W.stride(0), k_off, ptr(dA), dA.stride(0), M, N, K,
@@ -164,6 +203,7 @@ class LayerPlan:
         self.el_off = 2 * hf if self.res_mode == 1 else hf
         self.er_off = self.el_off + self.H
         self.ycols = self.er_off + self.H
+        self.wide = False            # set by StackPlan once the input widths are known
 
 
 class StackPlan:
@@ -182,6 +222,9 @@ class StackPlan:
                 off += self.widths[t]
             L.k_in = off
             L.in_offs = [sum(self.widths[t] for t in L.inputs[:j]) for j in range(len(L.inputs))]
+            k1 = self.widths[L.inputs[0]]
+            L.wide = (L.mean_heads and L.res_mode in (0, 1) and L.H in (1, 2, 4) and L.F % 32 == 0
+                      and L.H * L.F <= 4096 and len(L.inputs) <= 2 and k1 % 64 == 0 and L.H * L.F >= 4 * L.k_in)
 
     def supported(self):
         for L in self.layers:
@@ -230,7 +273,6 @@ def _forward(plan: StackPlan, graph, ext, packed, biases, head, training, keep):
                     raise SpgnnError(f"stack: tensor {t!r} consumed before it is produced")
                 variants[key] = split_planes(ext[t], pdrop[i], fseed[i], nch, off // 4)
             ins.append(variants[key])
-        Y = planes_linear(ins[0], packed[i], A2=ins[1] if len(ins) > 1 else None)
         # one planes copy of the output per distinct consumer mask (consumers without dropout share one)
         cons = plan.consumers.get(L.output, [])
         keys = []
@@ -243,6 +285,23 @@ def _forward(plan: StackPlan, graph, ext, packed, biases, head, training, keep):
             keys.append(-1)
         if len(keys) > 2:
             raise SpgnnError("stack: more than two dropout variants of one tensor are not supported")
+        if L.wide and WIDE_OUTPUT_LAYER and all(k < 0 for k in keys):
+            out32, P, rec = _wide_forward(L, graph, ins, packed[i], biases[i], conv, training, aseed[i], is_out,
+                                          bool(keys))
+            if P is not None:
+                variants[(L.output, -1)] = P
+            if is_out:
+                outs[L.output] = out32
+            if want_head:
+                emb_planes = P
+            if keep:
+                tape.layers[i] = rec
+            for t in L.inputs:
+                if all(ci <= i for ci, _ in plan.consumers[t]):
+                    for k in [k for k in variants if k[0] == t]:
+                        del variants[k]
+            continue
+        Y = planes_linear(ins[0], packed[i], A2=ins[1] if len(ins) > 1 else None)
         d = _Layer()
         d.in_ptr, d.in_src = ptr(graph.in_ptr), ptr(graph.in_src)
         d.N, d.H, d.F = N, L.H, L.F
@@ -291,6 +350,125 @@ def _forward(plan: StackPlan, graph, ext, packed, biases, head, training, keep):
     return logits, outs, tape
 
 
+class _WideRec:
+    """Tape record of a layer evaluated aggregate-first."""
+    __slots__ = ("XA", "att", "eler", "bias", "aseed", "kp")
+
+
+def _wide_desc(L, graph, conv, training, aseed, XA, kp, eler, att):
+    d = _Wide()
+    d.in_ptr, d.in_src = ptr(graph.in_ptr), ptr(graph.in_src)
+    d.out_ptr, d.out_dst, d.out_slot = ptr(graph.out_ptr), ptr(graph.out_dst), ptr(graph.out_slot)
+    d.N, d.H, d.has_res = graph.num_nodes, L.H, int(L.res_mode == 1)
+    d.eler, d.ld_eler = ptr(eler), eler.stride(0)
+    d.negative_slope = conv.negative_slope
+    d.attn_drop_p = conv.attn_drop_p if training else 0.0
+    d.attn_seed = aseed
+    d.att = ptr(att)
+    d.XA, d.ldxa, d.psxa, d.kp = XA.ptr(), XA.ld, XA.ps, kp
+    return d
+
+
+def _wide_forward(L, graph, ins, W, bias, conv, training, aseed, want_out, want_planes):
+    """Head-averaged output layer, aggregate-first (spgnn_gat_aggx_fwd + spgnn_wide_linear mode 0)."""
+    L_ = lib()
+    dev = graph.in_ptr.device
+    N, E, H, F = graph.num_nodes, graph.num_edges, L.H, L.F
+    hf, k_in = H * F, L.k_in
+    has_res = int(L.res_mode == 1)
+    kp = (k_in + 63) // 64 * 64
+    rows0 = hf * (1 + has_res)
+    eler = planes_linear(ins[0], W[rows0:rows0 + 2 * H], A2=ins[1] if len(ins) > 1 else None)
+    XA = Planes(N, (H + 1) * kp, dev)
+    att = torch.empty(E, H, dtype=torch.float32, device=dev)
+    d = _wide_desc(L, graph, conv, training, aseed, XA, kp, eler, att)
+    d.X1, d.ldx1, d.psx1, d.K1 = ins[0].ptr(), ins[0].ld, ins[0].ps, ins[0].cols
+    if len(ins) > 1:
+        d.X2, d.ldx2, d.psx2, d.K2 = ins[1].ptr(), ins[1].ld, ins[1].ps, ins[1].cols
+    L_.gat_aggx_fwd(ctypes.byref(d), stream(),
+                    _key=("bytes", 4.0 * N * (k_in + 2 * H) + 4.0 * N * (H + 1) * kp + 4.0 * (N + 1) + 4.0 * E))
+    out32 = ops.empty_padded(N, F, dev) if want_out else None
+    P = Planes(N, F, dev) if want_planes else None
+    ws = _ws(L_.wide_linear_ws(H, F, kp, has_res), dev)
+    L_.wide_linear(XA.ptr(), XA.ld, XA.ps, kp, k_in, N, H, F, has_res, ptr(W), W.stride(0), ptr(bias), conv._act, 0,
+                   ptr(out32), out32.stride(0) if out32 is not None else 0,
+                   P.ptr() if P is not None else None, P.ld if P is not None else 0, P.ps if P is not None else 0,
+                   None, 0, None, 0, None, 0, None, 0, 0, None, ptr(ws), ws.numel(), stream(),
+                   _key=("flops", 2.0 * N * hf * k_in * (1 + has_res)))
+    rec = _WideRec()
+    rec.XA, rec.att, rec.eler, rec.bias, rec.aseed, rec.kp = XA, att, eler, bias, aseed, kp
+    return out32, P, rec
+
+
+def _wide_backward(L, graph, rec, W, gsrcs, training, need_bias):
+    """Returns (d packed weight [ycols, k_in], d bias or None, dX fp32 [N, k_in])."""
+    L_ = lib()
+    dev = graph.in_ptr.device
+    N, E, H, F = graph.num_nodes, graph.num_edges, L.H, L.F
+    hf, k_in, kp = H * F, L.k_in, rec.kp
+    k4 = (k_in + 3) // 4 * 4
+    has_res = int(L.res_mode == 1)
+    conv = L.conv
+    if not 1 <= len(gsrcs) <= 3:
+        raise SpgnnError("stack: 1..3 gradient contributions to the output layer are supported")
+    XA = rec.XA
+    dpre = Planes(N, hf, dev)
+    db = torch.empty(hf, dtype=torch.float32, device=dev) if rec.bias is not None and need_bias else None
+    ws = _ws(L_.wide_linear_ws(H, F, kp, has_res), dev)
+    gp = [(ptr(g), g.stride(0)) for g in gsrcs] + [(None, 0)] * (3 - len(gsrcs))
+    L_.wide_linear(XA.ptr(), XA.ld, XA.ps, kp, k_in, N, H, F, has_res, ptr(W), W.stride(0), ptr(rec.bias), conv._act, 1,
+                   None, 0, None, 0, 0, gp[0][0], gp[0][1], gp[1][0], gp[1][1], gp[2][0], gp[2][1],
+                   dpre.ptr(), dpre.ld, dpre.ps, ptr(db), ptr(ws), ws.numel(), stream(),
+                   _key=("flops", 2.0 * N * hf * k_in * (1 + has_res)))
+    ldx = (1 + has_res) * k4
+    dXA = torch.empty(H, N, ldx, dtype=torch.float32, device=dev)
+    x_view = PlanesView(XA, H * kp, k_in)
+    dWz, dWres = [], []
+    pad = k4 - k_in
+    for h in range(H):
+        dpre_h = PlanesView(dpre, h * F, F)
+        dW_h = planes_linear_bwd_weight(dpre_h, PlanesView(XA, h * kp, k_in), x_view if has_res else None)
+        dWz.append(dW_h[:, :k_in])
+        blocks = [W[h * F:(h + 1) * F]] + ([W[hf + h * F:hf + (h + 1) * F]] if has_res else [])
+        if pad:
+            blocks = [torch.nn.functional.pad(b_, (0, pad)) for b_ in blocks]
+        Wcat = torch.cat(blocks, 1) if len(blocks) > 1 else blocks[0].contiguous()
+        planes_linear_bwd_input(dpre_h, Wcat, ldx, out=dXA[h])
+        if has_res:
+            dWres.append(dW_h[:, k_in:])
+    del dpre
+    rows0 = hf * (1 + has_res)
+    w_eler = ops._rows(W[rows0:rows0 + 2 * H])
+    if w_eler.stride(0) < k4:
+        w_eler = torch.nn.functional.pad(w_eler, (0, k4 - k_in))
+    d_eler = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
+    dep = Planes(N, 2 * H, dev)
+    ds = torch.empty(E * H, dtype=torch.float32, device=dev)
+    dX = ops.empty_padded(N, k_in, dev)
+    d = _wide_desc(L, graph, conv, training, rec.aseed, XA, kp, rec.eler, rec.att)
+    # the backward kernels read x from XA; X1/X2 only have to pass the descriptor checks
+    d.X1, d.ldx1, d.psx1 = XA.ptr(), XA.ld, XA.ps
+    d.X2, d.ldx2, d.psx2 = XA.ptr(), XA.ld, XA.ps
+    d.K1, d.K2 = _wide_k_split(L, k_in)
+    d.dXA, d.ld_dxa, d.head_stride = ptr(dXA), ldx, N * ldx
+    d.w_eler, d.ld_w = ptr(w_eler), w_eler.stride(0)
+    d.ds_ws = ptr(ds)
+    d.d_eler, d.ld_de = ptr(d_eler), d_eler.stride(0)
+    d.d_eler_planes, d.ld_dep, d.ps_dep = dep.ptr(), dep.ld, dep.ps
+    d.dX, d.ld_dx = ptr(dX), dX.stride(0)
+    L_.gat_aggx_bwd(ctypes.byref(d), stream(),
+                    _key=("bytes", 4.0 * N * (H * ldx + 2 * k_in + 4 * H) + 4.0 * N * H * k4 + 8.0 * (N + 1) + 12.0 * E))
+    dW_eler = planes_linear_bwd_weight(dep, x_view)
+    d_packed = torch.cat(dWz + dWres + [dW_eler], 0)
+    return d_packed, db, dX
+
+
+def _wide_k_split(L, k_in):
+    """(K1, K2) of the layer's concatenated input as the aggx descriptor wants them (K1 % 64 == 0)."""
+    k1 = L.in_offs[1] if len(L.in_offs) > 1 else k_in
+    return k1, k_in - k1
+
+
 def _grad_rows(g):
     """fp32 gradient tensor usable as a gradient source: unit inner stride, 16-byte aligned rows."""
     g = ops._rows(g)
@@ -324,8 +502,6 @@ def _backward(plan: StackPlan, graph, tape, packed, head, g_logits, g_outs, need
     for i in range(nL - 1, -1, -1):
         L = plan.layers[i]
         conv = L.conv
-        ins, Y, att, b = tape.layers[i]
-        tape.layers[i] = None
         srcs = []
         for ci, off in plan.consumers.get(L.output, []):
             if ci in dX and dX[ci] is not None and off < dX[ci].shape[1]:
@@ -334,10 +510,21 @@ def _backward(plan: StackPlan, graph, tape, packed, head, g_logits, g_outs, need
             srcs.append((g, 0, 0.0, 0, 1))
         if not srcs:
             dX[i] = None          # nothing flows into this layer: its parameters get no gradient
+            tape.layers[i] = None
             continue
         if len(srcs) > 3:
             raise SpgnnError("stack: more than three gradient contributions to one tensor are not supported")
         hf = L.H * L.F
+        if isinstance(tape.layers[i], _WideRec):
+            rec = tape.layers[i]
+            tape.layers[i] = None
+            if any(p > 0.0 or off for _, off, p, _, _ in srcs):
+                raise SpgnnError("stack: a head-averaged output layer cannot have masked gradient sources")
+            d_packed[i], d_bias[i], dX[i] = _wide_backward(L, graph, rec, packed[i], [g for g, *_ in srcs],
+                                                           tape.training, need_bias[i])
+            continue
+        ins, Y, att, b = tape.layers[i]
+        tape.layers[i] = None
         dY = Planes(N, L.ycols, dev)
         d = _Layer()
         d.in_ptr, d.in_src = ptr(graph.in_ptr), ptr(graph.in_src)

@@ -43,6 +43,9 @@ FULL_MODELS = {
     "st_pgat_spgnn_3": ("spgnn", dict(FULL_COMMON, num_gat_layers=3, num_heads=2, num_out_heads=2, feat_drop=0.1,
                                       attn_drop=0.1, negative_slope=0.2, pos_hiddens=[256, 128, 64],
                                       num_pos_heads=1, pos_enc_dim=39)),
+    "st_pgat_spgnnnl_3": ("spgnn", dict(FULL_COMMON, num_gat_layers=3, num_heads=2, num_out_heads=2, feat_drop=0.1,
+                                        attn_drop=0.1, negative_slope=0.2, pos_hiddens=[256, 128, 64],
+                                        num_pos_heads=1, pos_enc_dim=39, mode="PENL")),
 }
 
 

@@ -81,7 +81,8 @@ def test_models_construct_with_reference_settings_and_dgl_state_dict_names():
     from spgnn_b200 import models as sm
     from helpers import FULL_MODELS
     counts = {"st_pgat_spgnn_3": 2_501_078, "st_gat_3": 1_931_926, "st_gat_6": 2_031_382, "st_gat_6_nr": 1_031_958,
-              "st_gcn_3": 392_662, "st_gin_3": 1_537_955, "st_sage_3": 1_897_366}
+              "st_gcn_3": 392_662, "st_gin_3": 1_537_955, "st_sage_3": 1_897_366,
+              "st_pgat_spgnnnl_3": 2_161_558}
     cls = {"gat": sm.GATNet, "gcn": sm.GCNNet, "gin": sm.GINNet, "sage": sm.SAGENet, "spgnn": sm.GATPositionSPGNNNet}
     for name, (kind, cfg) in FULL_MODELS.items():
         # the CNN-trunk keys of settings.MODEL are accepted and ignored

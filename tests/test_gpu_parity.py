@@ -238,6 +238,56 @@ def test_full_width_forward_backward_vs_oracle(mods, name, mode, monkeypatch):
             (name, k, rel_err(p.grad.cpu(), r), abs_err, gmax)
 
 
+@pytest.mark.parametrize("name", ["st_gat_3", "st_gat_6_nr", "st_pgat_spgnn_3", "st_pgat_spgnnnl_3"])
+@pytest.mark.parametrize("train", [False, True])
+def test_aggregate_first_output_layer_equals_projection_first(mods, name, train, monkeypatch):
+    """The head-averaged output layer evaluated aggregate-first (spgnn_gat_aggx_* + spgnn_wide_linear) against the
+    projection-first layer kernels on the same weights, inputs and dropout seeds: outputs and every parameter
+    gradient agree to fp32 round-off (both paths hold the 1e-4 bar against the oracle separately).  In train mode
+    the output layer gets attention dropout as well, so the regenerated masks of both paths are compared too."""
+    from spgnn_b200 import stack
+    kind, cfg = FULL_MODELS[name]
+    scans = _scan_dicts(mods, 2000, 5, ragged=True)
+    pos = None
+    if kind == "spgnn":
+        pos = np.concatenate([mods["ope"].dist_pos_enc(s["adj"], mods["ope"].anchors_39(s["fvs_out"], s["adj"]))[0]
+                              for s in scans])
+    torch.manual_seed(3)
+    net = getattr(mods["sm"], NET_CLS[kind])(**cfg).cuda()
+    net.init()
+    with torch.no_grad():
+        for k, p_ in net.named_parameters():
+            if k.endswith("bias"):
+                p_.normal_(0, 0.05)
+    net.set_gcn_only()
+    net.train(train)
+    if train:
+        net.gat.gat_layers[-1].attn_drop_p = 0.2
+    g = _device_batch(mods, scans, pos)
+    y = torch.from_numpy(np.concatenate([s["labels"] for s in scans])).cuda()
+    cw = torch.tensor([0.2] + [0.8] * 21).cuda()
+    res = {}
+    for wide in (True, False):
+        monkeypatch.setattr(stack, "WIDE_OUTPUT_LAYER", wide)
+        mods["ops"].manual_seed(11)
+        net.zero_grad()
+        out = net(g)
+        loss = mods["ops"].masked_cross_entropy(out[0], y, cw, mask=torch.ones_like(y, dtype=torch.bool))
+        (loss + 1e-3 * out[1].square().mean()).backward()
+        res[wide] = ([o.detach().clone() for o in out], {k: p_.grad.clone() for k, p_ in net.named_parameters()
+                                                         if p_.grad is not None})
+    plan = net.gat._stack_plan()
+    assert plan.layers[-1].wide, "the output layer of this preset should qualify for the aggregate-first path"
+    for a, b in zip(res[True][0], res[False][0]):
+        assert rel_err(a.cpu(), b.cpu()) < 2e-5, name
+    gmax = max(float(v.abs().max()) for v in res[False][1].values())
+    assert set(res[True][1]) == set(res[False][1])
+    for k, b in res[False][1].items():
+        a = res[True][1][k]
+        abs_err = float((a.double() - b.double()).abs().max())
+        assert abs_err <= 5e-5 * float(b.abs().max()) or abs_err <= 1e-6 * gmax, (name, k, abs_err, float(b.abs().max()))
+
+
 def test_state_dict_keys_are_dgl_names(mods):
     kind, cfg = FULL_MODELS["st_pgat_spgnn_3"]
     net = mods["sm"].GATPositionSPGNNNet(**cfg)
