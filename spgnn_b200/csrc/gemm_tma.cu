@@ -244,7 +244,7 @@ struct WideArgs {
     int kbp, nparts, kp;
     int stages, stage_bytes;
 };
-constexpr int kWideEpiWarps = 8;                       // two warps per TMEM lane quadrant, alternating column chunks
+constexpr int kWideEpiWarps = 16;                      // four warps per TMEM lane quadrant, interleaved column chunks
 constexpr int kWideThreads = (kWideEpiWarps + 2) * 32;
 constexpr int kWideStgBytes = kWideEpiWarps * 32 * 16 * 4;   // one swizzled 32 x 16 fp32 tile per epilogue warp
 constexpr int kWideFixed = 1024 /*align*/ + 256 /*barriers*/ + kWideStgBytes;
@@ -274,30 +274,43 @@ __device__ __forceinline__ void st_planes4(__nv_bfloat16* q, int64_t ps, float4 
 // the incoming gradient of the warp's four chunks is loaded BEFORE waiting for the accumulator, so its DRAM latency
 // hides behind the MMAs of this tile.
 template <int ACT>
-__device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg, float* sb, uint32_t taddr, int64_t m0,
-                                                   int n0, int ncols, int warp, int lane, uint32_t full_bar,
-                                                   uint32_t full_par) {
-    const int quad = warp & 3, half = warp >> 2;
+__device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg, float* dbias_row, uint32_t taddr,
+                                                   int64_t m0, int n0, int ncols, int warp, int lane,
+                                                   uint32_t full_bar, uint32_t full_par) {
+    const int quad = warp & 3, part = warp >> 2;
     const int r0 = lane >> 2, cq = lane & 3;
     const float inv_h = 1.f / (float)g.H;
     const int64_t row0 = m0 + quad * 32 + r0;
     const int nrow = (int)max((int64_t)0, min((int64_t)4, (g.M - row0 + 7) / 8));
     for (int cg = 0; cg < ncols; cg += 128) {
-        float4 run[4][4];
+        float4 run[2][4];
+        // gradient of the warp's four chunks: every load is issued before the first use (16 independent 16-byte
+        // loads in flight per thread), then the optional further sources are added chunk by chunk
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c0 = cg + q * 32 + half * 16;
+        for (int q = 0; q < 2; ++q) {
+            const int c0 = cg + q * 64 + part * 16;
             const int col = n0 + c0 + cq * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 run[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.mode == 1 && i < nrow && c0 < ncols) {
-                    const int64_t r = row0 + 8 * i;
-                    for (int s = 0; s < g.n_g; ++s) {
-                        const float4 t = ldg4(g.g[s] + r * g.ldg[s] + col);
-                        run[q][i].x += t.x; run[q][i].y += t.y; run[q][i].z += t.z; run[q][i].w += t.w;
+                if (g.mode == 1 && i < nrow && c0 < ncols) run[q][i] = ldg4(g.g[0] + (row0 + 8 * i) * g.ldg[0] + col);
+            }
+        }
+        if (g.mode == 1) {
+            for (int s = 1; s < g.n_g; ++s) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c0 = cg + q * 64 + part * 16;
+                    const int col = n0 + c0 + cq * 4;
+                    float4 t[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        t[i] = (i < nrow && c0 < ncols) ? ldg4(g.g[s] + (row0 + 8 * i) * g.ldg[s] + col)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        run[q][i].x += t[i].x; run[q][i].y += t[i].y; run[q][i].z += t[i].z; run[q][i].w += t[i].w;
                     }
-                    run[q][i].x *= inv_h; run[q][i].y *= inv_h; run[q][i].z *= inv_h; run[q][i].w *= inv_h;
                 }
             }
         }
@@ -306,13 +319,14 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
             tc_fence_after();
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c0 = cg + q * 32 + half * 16;
+        for (int q = 0; q < 2; ++q) {
+            const int c0 = cg + q * 64 + part * 16;
             if (c0 >= ncols) break;
             const int col = n0 + c0 + cq * 4;
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
             for (int h = 0; h < g.H; ++h) {
-                uint32_t v[16];
-                tmem_ld16(taddr + h * g.BN + c0, v);
+                const float4 bv = g.bias ? ldg4(g.bias + h * g.F + col) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -320,7 +334,7 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
                         make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 __syncwarp();
-                const float4 bv = g.bias ? ldg4(g.bias + h * g.F + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (h + 1 < g.H) tmem_ld16(taddr + (h + 1) * g.BN + c0, v);      // next head: in flight during the math
                 float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -334,22 +348,22 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
                         run[q][i].x += x.x; run[q][i].y += x.y; run[q][i].z += x.z; run[q][i].w += x.w;
                     } else if (i < nrow) {
                         float4 d;
-                        d.x = run[q][i].x * wide_act_grad<ACT>(x.x, g.act);
-                        d.y = run[q][i].y * wide_act_grad<ACT>(x.y, g.act);
-                        d.z = run[q][i].z * wide_act_grad<ACT>(x.z, g.act);
-                        d.w = run[q][i].w * wide_act_grad<ACT>(x.w, g.act);
+                        d.x = run[q][i].x * inv_h * wide_act_grad<ACT>(x.x, g.act);
+                        d.y = run[q][i].y * inv_h * wide_act_grad<ACT>(x.y, g.act);
+                        d.z = run[q][i].z * inv_h * wide_act_grad<ACT>(x.z, g.act);
+                        d.w = run[q][i].w * inv_h * wide_act_grad<ACT>(x.w, g.act);
                         st_planes4(g.dpre + (row0 + 8 * i) * g.ldd + h * g.F + col, g.psd, d);
                         bs.x += d.x; bs.y += d.y; bs.z += d.z; bs.w += d.w;
                     }
                 }
-                if (g.mode == 1 && g.dbias_ws) {
+                if (g.mode == 1 && dbias_row) {
 #pragma unroll
                     for (int o = 4; o < 32; o <<= 1) {
                         bs.x += __shfl_xor_sync(kFull, bs.x, o); bs.y += __shfl_xor_sync(kFull, bs.y, o);
                         bs.z += __shfl_xor_sync(kFull, bs.z, o); bs.w += __shfl_xor_sync(kFull, bs.w, o);
                     }
-                    if (lane < 4) {
-                        float* p = sb + h * g.F + col;
+                    if (lane < 4) {                       // this CTA's partial row (L2 reductions, no return value)
+                        float* p = dbias_row + h * g.F + col;
                         atomicAdd(p, bs.x); atomicAdd(p + 1, bs.y); atomicAdd(p + 2, bs.z); atomicAdd(p + 3, bs.w);
                     }
                 }
@@ -376,10 +390,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int stages_bytes = g.stages * g.stage_bytes;
     NtShared* sh = reinterpret_cast<NtShared*>(smem + stages_bytes);
-    float* sb = reinterpret_cast<float*>(smem + stages_bytes + 256 + kWideStgBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const int HF = g.H * g.F;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
@@ -392,8 +404,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
         }
         fence_barrier_init();
     }
-    if (g.dbias_ws)
-        for (int i = threadIdx.x; i < HF; i += kWideThreads) sb[i] = 0.f;
     if (warp == kWideEpiWarps + 1 && lane == 0) {
         prefetch_tmap(&maps.a);
         prefetch_tmap(&maps.b);
@@ -412,6 +422,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
         // ===================================================== epilogue
         int it = 0;
         float* stg = reinterpret_cast<float*>(smem + stages_bytes + 256) + warp * (32 * 16);
+        float* dbias_row = g.dbias_ws ? g.dbias_ws + (int64_t)blockIdx.x * (g.H * g.F) : nullptr;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t par = (it >> 1) & 1;
@@ -420,9 +431,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
             const int ncols = min(g.BN, g.F - n0);
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * accw);
             const uint32_t fb = smem_u32(&sh->tmem_full[buf]);
-            if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU>(g, stg, sb, taddr, m0, n0, ncols, warp, lane, fb, par);
-            else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE>(g, stg, sb, taddr, m0, n0, ncols, warp, lane, fb, par);
-            else wide_epilogue_tile<-1>(g, stg, sb, taddr, m0, n0, ncols, warp, lane, fb, par);
+            if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+            else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+            else wide_epilogue_tile<-1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
             tc_fence_before();
             mbar_arrive(smem_u32(&sh->tmem_empty[buf]));
         }
@@ -491,8 +502,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
 
     tc_fence_before();
     __syncthreads();
-    if (g.dbias_ws)
-        for (int i = threadIdx.x; i < HF; i += kWideThreads) g.dbias_ws[(int64_t)blockIdx.x * HF + i] = sb[i];
     if (warp == kWideEpiWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -895,7 +904,7 @@ extern "C" int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa,
                                  int64_t ws_bytes, void* stream) {
     SPGNN_REQUIRE(XA && W && ws && M > 0 && k_in > 0, "wide_linear: bad argument");
     SPGNN_REQUIRE(H == 1 || H == 2 || H == 4, "wide_linear: H must be 1, 2 or 4 (got %d)", H);
-    SPGNN_REQUIRE(F > 0 && F % 32 == 0 && (int64_t)H * F <= 4096, "wide_linear: F (%d) must be a multiple of 32, H*F <= 4096", F);
+    SPGNN_REQUIRE(F > 0 && F % 32 == 0 && (int64_t)H * F <= 8192, "wide_linear: F (%d) must be a multiple of 32, H*F <= 8192", F);
     SPGNN_REQUIRE(kp % BK == 0 && kp >= k_in && ldxa >= (H + 1) * kp && ldw >= k_in, "wide_linear: kp / ld mismatch");
     SPGNN_REQUIRE(mode == 0 || mode == 1, "wide_linear: mode must be 0 (forward) or 1 (gradient of the pre-activations)");
     SPGNN_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "wide_linear: bias must be 16-byte aligned");
@@ -949,7 +958,7 @@ extern "C" int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa,
     rc = make_planes_map(&maps.b, hi, HF, ldb, ldb, HF * ldb, BK, a.BN);
     if (rc) return rc;
     a.stage_bytes = kABytes + a.BN * 256;
-    const int fixed = kWideFixed + (int)HF * 4;
+    const int fixed = kWideFixed;
     a.stages = (kSmemLimit - fixed) / a.stage_bytes;
     if (a.stages > kMaxStages) a.stages = kMaxStages;
     SPGNN_REQUIRE(a.stages >= 2, "wide_linear: not enough shared memory for two pipeline stages");
@@ -959,6 +968,7 @@ extern "C" int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa,
     if (mode == 1 && dbias) {
         part = reinterpret_cast<float*>(((uintptr_t)(hi + 2 * HF * ldb) + 255) & ~(uintptr_t)255);
         a.dbias_ws = part;
+        SPGNN_CUDA_OK(cudaMemsetAsync(part, 0, (size_t)grid * HF * sizeof(float), st));
     }
     wide_kernel<<<grid, kWideThreads, kSmemLimit, st>>>(maps, a);
     SPGNN_LAUNCH_OK();

@@ -224,7 +224,7 @@ class StackPlan:
             L.in_offs = [sum(self.widths[t] for t in L.inputs[:j]) for j in range(len(L.inputs))]
             k1 = self.widths[L.inputs[0]]
             L.wide = (L.mean_heads and L.res_mode in (0, 1) and L.H in (1, 2, 4) and L.F % 32 == 0
-                      and L.H * L.F <= 4096 and len(L.inputs) <= 2 and k1 % 64 == 0 and L.H * L.F >= 4 * L.k_in)
+                      and L.H * L.F <= 8192 and len(L.inputs) <= 2 and k1 % 64 == 0 and L.H * L.F >= 4 * L.k_in)
 
     def supported(self):
         for L in self.layers:
