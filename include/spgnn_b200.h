@@ -77,7 +77,8 @@ int spgnn_adj_fill(const uint8_t* adj, const int64_t* adj_off, const int64_t* n_
  *        node_gid int32 [N];
  *        in_ptr int32 [N+1], in_src int32 [E], in_eid int32 [E]   — in-edges of each node, ascending edge id
  *        out_ptr int32 [N+1], out_dst int32 [E], out_slot int32 [E] — out-edges; out_slot = position in in_* arrays
- *        flags int32 [2]: [0] = number of zero-in-degree nodes, [1] = number of out-of-range endpoints
+ *        flags int32 [4]: [0] = number of zero-in-degree nodes, [1] = number of out-of-range endpoints,
+ *        [2] = largest in-degree, [3] = largest out-degree
  *   ws : spgnn_batch_ws_bytes(N, E) bytes of scratch. */
 int64_t spgnn_batch_ws_bytes(int64_t N, int64_t E);
 int spgnn_batch_build(const int64_t* node_off, const int64_t* edge_off, int64_t B, int64_t N, int64_t E,
@@ -235,6 +236,12 @@ typedef struct spgnn_gat_layer {
     int32_t n_gsrc; int32_t reserved2; spgnn_gsrc gsrc[3];
     uint16_t* dY_hi; int64_t dY_ld; int64_t dY_ps;
     float* g_ws; float* ds_ws; float* dbias; float* dbias_ws;
+    /* optional: per-graph node offsets [B+1] (int64) and the largest graph of the batch.  When given (and F % 64
+     * == 0, no head mean, the largest graph fits in shared memory) the layer runs one CTA per graph with the
+     * graph's z rows staged in shared memory by TMA, 64 columns at a time: every neighbour gather is a shared-memory
+     * read and DRAM traffic equals the algorithmic bytes; the backward then fuses the destination and source sides.
+     * max_degree = largest in- or out-degree of the batch (spgnn_batch_build flags[2], flags[3]); 0 = unknown. */
+    const int64_t* node_off; int64_t B; int64_t max_nodes; int64_t max_degree;
 } spgnn_gat_layer;
 int64_t spgnn_gat_layer_sizeof(void);
 int64_t spgnn_gat_layer_dbias_ws(int64_t N, int64_t H, int64_t F);

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libspgnn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-          "--expt-extended-lambda", "-Xptxas", "-v"]
+          "--expt-extended-lambda", "-Xptxas", "-v"] + os.environ.get("SPGNN_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -17,32 +17,12 @@
 
 namespace spgnn {
 namespace layer {
-constexpr int kNPC = 128;        // nodes per CTA chunk
+#ifndef SPGNN_NPC
+#define SPGNN_NPC 128
+#endif
+constexpr int kNPC = SPGNN_NPC;  // nodes per CTA chunk
 constexpr int kThreads = 256;
 constexpr int kMaxH = 8;
-
-struct Sink {
-    __nv_bfloat16* hi; int64_t ld, ps; int64_t nch, ch_off; uint32_t thr; float scale; uint64_t seed;
-};
-struct GSrc {
-    const float* g; int64_t ld; int64_t nch, ch_off; uint32_t thr; float scale; uint64_t seed;
-};
-struct Args {
-    const int32_t *in_ptr, *in_src, *out_ptr, *out_dst, *out_slot;
-    int64_t N; int H, F;
-    const float* Y; int64_t ldy, res_off, el_off, er_off; int res_mode, act; float neg_slope; int mean_heads;
-    const float* bias; float drop_p; uint64_t seed;
-    float* att;
-    float* out; int64_t ldo; int n_sinks; Sink sinks[2];
-    int n_g; GSrc gs[3];
-    __nv_bfloat16* dY; int64_t dld, dps;
-    float* g_ws; float* ds; float* dbias_ws;
-};
-
-__device__ __forceinline__ float keep_scale(const Args& a, int64_t slot, int h) {
-    if (a.drop_p <= 0.f) return 1.f;
-    return u01(a.seed, (uint64_t)slot * (uint64_t)a.H + (uint64_t)h) >= a.drop_p ? 1.f / (1.f - a.drop_p) : 0.f;
-}
 
 // shared-memory staging of one chunk
 struct Stage {
@@ -74,15 +54,6 @@ static size_t stage_bytes(int H, int HF, bool bwd_dst) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__device__ __forceinline__ void emit(const Args& a, int64_t v, int c, float4 y) {
-    if (a.out) st4(a.out + v * a.ldo + c, y);
-    for (int s = 0; s < a.n_sinks; ++s) {
-        const Sink& k = a.sinks[s];
-        const float4 d = drop4(y, k.thr, k.scale, k.seed, (uint64_t)v * (uint64_t)k.nch + (uint64_t)(k.ch_off + (c >> 2)));
-        store_planes4(k.hi + v * k.ld + c, k.ps, d);
-    }
-}
-
 __global__ void __launch_bounds__(kThreads) gat_layer_fwd_kernel(const Args a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const Stage st = carve(smem, a.H, a.H * a.F);
@@ -202,15 +173,6 @@ __global__ void __launch_bounds__(kThreads) gat_layer_fwd_kernel(const Args a) {
 
 // ------------------------------------------------------------------------------------------------ backward, dst side
 // gradient of the layer output chunk (v, columns c..c+3): sum over consumers of mask * d(consumer input)
-__device__ __forceinline__ float4 load_g(const Args& a, int64_t v, int c) {
-    float4 g = zero4();
-    for (int s = 0; s < a.n_g; ++s) {
-        const GSrc& k = a.gs[s];
-        const float4 t = ldg4(k.g + v * k.ld + c);
-        g = add4(g, drop4(t, k.thr, k.scale, k.seed, (uint64_t)v * (uint64_t)k.nch + (uint64_t)(k.ch_off + (c >> 2))));
-    }
-    return g;
-}
 __device__ __forceinline__ void store_G(const Args& a, int64_t v, int hc, float4 g) {
     if (a.res_mode == 1) store_planes4(a.dY + v * a.dld + a.res_off + hc, a.dps, g);
     else st4(a.g_ws + v * (int64_t)(a.H * a.F) + hc, g);
@@ -456,27 +418,14 @@ static unsigned layer_grid(int64_t N) {
     return (unsigned)(chunks < cap ? chunks : cap);
 }
 
-static uint32_t thr_of(float p) { return p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u; }
-
-static int fill_common(Args& a, const spgnn_gat_layer* L) {
-    SPGNN_REQUIRE(L, "gat_layer: null descriptor");
-    SPGNN_REQUIRE(L->in_ptr && L->in_src && L->Y && L->att && L->N > 0 && L->H > 0 && L->H <= kMaxH && L->F > 0,
-                  "gat_layer: bad argument (N=%lld H=%d F=%d)", (long long)L->N, (int)L->H, (int)L->F);
-    SPGNN_REQUIRE(L->F % 4 == 0 && L->ldy % 4 == 0 && ((uintptr_t)L->Y & 15) == 0 && L->res_off % 4 == 0,
-                  "gat_layer: F (%d), ldy (%lld) and res_off must be multiples of 4 and Y 16-byte aligned", (int)L->F,
-                  (long long)L->ldy);
-    SPGNN_REQUIRE(L->res_mode == 0 || L->res_mode == 1, "gat_layer: res_mode must be 0 (none) or 1 (linear, in Y)");
-    SPGNN_REQUIRE(!L->bias || ((uintptr_t)L->bias & 15) == 0, "gat_layer: bias must be 16-byte aligned");
-    SPGNN_REQUIRE(L->attn_drop_p >= 0.f && L->attn_drop_p < 1.f, "gat_layer: attention dropout p");
-    a.in_ptr = L->in_ptr; a.in_src = L->in_src; a.out_ptr = L->out_ptr; a.out_dst = L->out_dst; a.out_slot = L->out_slot;
-    a.N = L->N; a.H = L->H; a.F = L->F;
-    a.Y = L->Y; a.ldy = L->ldy; a.res_off = L->res_off; a.el_off = L->el_off; a.er_off = L->er_off;
-    a.res_mode = L->res_mode; a.act = L->act; a.neg_slope = L->negative_slope; a.mean_heads = L->mean_heads;
-    a.bias = L->bias; a.drop_p = L->attn_drop_p; a.seed = L->attn_seed; a.att = L->att;
-    return SPGNN_OK;
-}
-
 }  // namespace layer
+}  // namespace spgnn
+
+namespace spgnn {
+namespace tree {
+int launch_fwd(const layer::Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* handled);
+int launch_bwd(const layer::Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* handled);
+}
 }  // namespace spgnn
 
 using namespace spgnn;
@@ -504,6 +453,9 @@ extern "C" int spgnn_gat_layer_fwd(const spgnn_gat_layer* L, void* stream) {
         a.sinks[s] = Sink{reinterpret_cast<__nv_bfloat16*>(k.hi), k.ld, k.plane_stride, k.concat_chunks, k.chunk_off,
                           thr_of(k.drop_p), k.drop_p > 0.f ? 1.f / (1.f - k.drop_p) : 1.f, k.seed};
     }
+    bool handled = false;
+    rc = tree::launch_fwd(a, L, as_stream(stream), &handled);
+    if (rc || handled) return rc;
     const size_t smem = stage_bytes(a.H, a.H * a.F, false);
     gat_layer_fwd_kernel<<<layer_grid(a.N), kThreads, smem, as_stream(stream)>>>(a);
     SPGNN_LAUNCH_OK();
@@ -533,6 +485,9 @@ extern "C" int spgnn_gat_layer_bwd(const spgnn_gat_layer* L, void* stream) {
     a.g_ws = L->g_ws; a.ds = L->ds_ws; a.dbias_ws = L->dbias ? L->dbias_ws : nullptr;
     SPGNN_REQUIRE(!L->dbias || L->dbias_ws, "gat_layer_bwd: dbias needs dbias_ws (spgnn_gat_layer_dbias_ws bytes)");
     cudaStream_t st = as_stream(stream);
+    bool handled = false;
+    rc = tree::launch_bwd(a, L, st, &handled);
+    if (rc || handled) return rc;
     const unsigned grid = layer_grid(a.N);
     const size_t smem_dst = stage_bytes(a.H, HF, true);
     static bool attr = false;

@@ -156,6 +156,7 @@ __global__ void k_sort_in(const int64_t* __restrict__ src, const int32_t* __rest
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < N; v += (int64_t)gridDim.x * blockDim.x) {
         int32_t b = in_ptr[v], e = in_ptr[v + 1];
         if (e == b) atomicAdd(&flags[0], 1);
+        if (e - b > *reinterpret_cast<volatile int32_t*>(flags + 2)) atomicMax(&flags[2], e - b);     // monotone: mostly skipped
         for (int32_t i = b + 1; i < e; ++i) {
             int32_t key = in_eid[i];
             int32_t j = i - 1;
@@ -177,9 +178,10 @@ __global__ void k_fill_out(const int32_t* __restrict__ in_src, int64_t E, const 
 
 __global__ void k_sort_out(const int64_t* __restrict__ dst, const int32_t* __restrict__ in_eid,
                            const int32_t* __restrict__ out_ptr, int64_t N, int32_t* __restrict__ out_slot,
-                           int32_t* __restrict__ out_dst) {
+                           int32_t* __restrict__ out_dst, int32_t* __restrict__ flags) {
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < N; u += (int64_t)gridDim.x * blockDim.x) {
         int32_t b = out_ptr[u], e = out_ptr[u + 1];
+        if (e - b > *reinterpret_cast<volatile int32_t*>(flags + 3)) atomicMax(&flags[3], e - b);
         for (int32_t i = b + 1; i < e; ++i) {
             int32_t key = out_slot[i];
             int32_t j = i - 1;
@@ -316,7 +318,7 @@ extern "C" int spgnn_batch_build(const int64_t* node_off, const int64_t* edge_of
     int32_t* cur_out = (int32_t*)(w + 3 * seg);
     int64_t* scan_ws = (int64_t*)(w + 4 * seg);
     SPGNN_CUDA_OK(cudaMemsetAsync(w, 0, 4 * seg, st));
-    SPGNN_CUDA_OK(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), st));
+    SPGNN_CUDA_OK(cudaMemsetAsync(flags, 0, 4 * sizeof(int32_t), st));
 
     k_node_gid<<<grid_for(N, 256), 256, 0, st>>>(node_off, B, N, node_gid);
     SPGNN_LAUNCH_OK();
@@ -333,7 +335,7 @@ extern "C" int spgnn_batch_build(const int64_t* node_off, const int64_t* edge_of
     SPGNN_LAUNCH_OK();
     k_fill_out<<<grid_for(E, 256), 256, 0, st>>>(in_src, E, out_ptr, cur_out, out_slot);
     SPGNN_LAUNCH_OK();
-    k_sort_out<<<grid_for(N, 128), 128, 0, st>>>(dst, in_eid, out_ptr, N, out_slot, out_dst);
+    k_sort_out<<<grid_for(N, 128), 128, 0, st>>>(dst, in_eid, out_ptr, N, out_slot, out_dst, flags);
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }

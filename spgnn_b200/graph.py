@@ -63,19 +63,17 @@ class Graph:
         g.node_gid = torch.empty(N, **i32)
         g.in_ptr, g.in_src, g.in_eid = torch.empty(N + 1, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
         g.out_ptr, g.out_dst, g.out_slot = torch.empty(N + 1, **i32), torch.empty(E, **i32), torch.empty(E, **i32)
-        flags = torch.empty(2, **i32)
+        flags = torch.empty(4, **i32)
         ws = torch.empty(int(lib().batch_ws_bytes(N, E)), dtype=torch.uint8, device=dev)
         lib().batch_build(ptr(g.node_off), ptr(g.edge_off), B, N, E, ptr(g.src_local), ptr(g.dst_local),
                           ptr(g.src), ptr(g.dst), ptr(g.node_gid), ptr(g.in_ptr), ptr(g.in_src), ptr(g.in_eid),
                           ptr(g.out_ptr), ptr(g.out_dst), ptr(g.out_slot), ptr(flags), ptr(ws), stream())
         g._flags = flags
+        g.zero_in_degree = g._max_degree = None
         if check:
-            f = flags.tolist()
+            f = g._read_flags()
             if f[1]:
                 raise SpgnnError(f"{f[1]} edge endpoints are outside their graph's node range")
-            g.zero_in_degree = f[0]
-        else:
-            g.zero_in_degree = None
         g.max_nodes = int(g._bnn.max().item()) if max_nodes is None else int(max_nodes)
         return g
 
@@ -143,9 +141,21 @@ class Graph:
             self._norms = (o_s, i_s, i_i, o_i)
         return self._norms
 
+    def _read_flags(self):
+        """One device→host read of the batch builder's flags (zero in-degree count, bad endpoints, max degrees)."""
+        f = self._flags.tolist()
+        self.zero_in_degree, self._max_degree = f[0], max(f[2], f[3])
+        return f
+
+    def max_degree(self):
+        """Largest in- or out-degree of the batch (airway trees with self loops: 4)."""
+        if self._max_degree is None:
+            self._read_flags()
+        return self._max_degree
+
     def check_no_zero_in_degree(self):
         if self.zero_in_degree is None:
-            self.zero_in_degree = int(self._flags[0].item())
+            self._read_flags()
         if self.zero_in_degree:
             raise SpgnnError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid "
                              "(DGLError in the reference stack); add self loops or pass allow_zero_in_degree=True")

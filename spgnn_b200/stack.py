@@ -52,7 +52,9 @@ class _Layer(ctypes.Structure):
                 ("n_gsrc", ctypes.c_int32), ("reserved2", ctypes.c_int32), ("gsrc", _GSrc * 3),
                 ("dY_hi", ctypes.c_void_p), ("dY_ld", ctypes.c_int64), ("dY_ps", ctypes.c_int64),
                 ("g_ws", ctypes.c_void_p), ("ds_ws", ctypes.c_void_p), ("dbias", ctypes.c_void_p),
-                ("dbias_ws", ctypes.c_void_p)]
+                ("dbias_ws", ctypes.c_void_p),
+                ("node_off", ctypes.c_void_p), ("B", ctypes.c_int64), ("max_nodes", ctypes.c_int64),
+                ("max_degree", ctypes.c_int64)]
 
 
 class _Wide(ctypes.Structure):
@@ -77,6 +79,8 @@ class _Wide(ctypes.Structure):
 # Aggregate-first evaluation of head-averaged output layers (include/spgnn_b200.h, spgnn_gat_wide).  Switch off to
 # run every layer through the projection-first kernels (tests compare the two).
 WIDE_OUTPUT_LAYER = True
+# One CTA per graph with the graph's rows staged in shared memory (spgnn_gat_layer.node_off).  Off: chunk kernels.
+TREE_KERNELS = True
 
 _checked = False
 
@@ -153,7 +157,10 @@ def planes_linear(A1: Planes, W, bias=None, act=0, slope=0.0, A2: Planes | None 
     K1, K2 = A1.cols, (A2.cols if A2 is not None else 0)
     if W.shape[1] != K1 + K2:
         raise SpgnnError(f"planes_linear: weight has {W.shape[1]} columns, input has {K1}+{K2}")
-    C = ops.empty_padded(M, N, W.device)
+    # rows padded to 128 bytes once they are wide enough to be sliced by the per-tree layer kernels (TMA boxes of 32
+    # columns then start on cache-line boundaries)
+    C = ops.empty_padded(M, N, W.device) if N < 64 else torch.empty(
+        M, (N + 31) // 32 * 32, dtype=torch.float32, device=W.device)[:, :N]
     L = lib()
     ws = _ws(L.planes_linear_fwd_ws(N, K1, K2), W.device)
     L.planes_linear_fwd(A1.ptr(), A1.ld, A1.ps, K1, A2.ptr() if A2 is not None else None,
@@ -305,6 +312,9 @@ def _forward(plan: StackPlan, graph, ext, packed, biases, head, training, keep):
         d = _Layer()
         d.in_ptr, d.in_src = ptr(graph.in_ptr), ptr(graph.in_src)
         d.N, d.H, d.F = N, L.H, L.F
+        if TREE_KERNELS:
+            d.node_off, d.B, d.max_nodes = ptr(graph.node_off), graph.batch_size, graph.max_nodes
+            d.max_degree = graph.max_degree()
         d.Y, d.ldy, d.res_off, d.el_off, d.er_off = ptr(Y), Y.stride(0), L.res_off, L.el_off, L.er_off
         d.res_mode, d.act, d.negative_slope, d.mean_heads = L.res_mode, conv._act, conv.negative_slope, int(L.mean_heads)
         b = biases[i]
@@ -530,6 +540,9 @@ def _backward(plan: StackPlan, graph, tape, packed, head, g_logits, g_outs, need
         d.in_ptr, d.in_src = ptr(graph.in_ptr), ptr(graph.in_src)
         d.out_ptr, d.out_dst, d.out_slot = ptr(graph.out_ptr), ptr(graph.out_dst), ptr(graph.out_slot)
         d.N, d.H, d.F = N, L.H, L.F
+        if TREE_KERNELS:
+            d.node_off, d.B, d.max_nodes = ptr(graph.node_off), graph.batch_size, graph.max_nodes
+            d.max_degree = graph.max_degree()
         d.Y, d.ldy, d.res_off, d.el_off, d.er_off = ptr(Y), Y.stride(0), L.res_off, L.el_off, L.er_off
         d.res_mode, d.act, d.negative_slope, d.mean_heads = L.res_mode, conv._act, conv.negative_slope, int(L.mean_heads)
         d.bias = ptr(b)
