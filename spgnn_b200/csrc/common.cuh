@@ -70,9 +70,15 @@ __device__ __forceinline__ float act_fwd(float x, int act, float slope) {
 }
 // lean variants for the bandwidth-bound aggregation kernels (a handful of instructions instead of the libm
 // expansions; absolute error ~1e-7, far inside the 1e-4 parity bar)
+// exp(x) as one FMUL + MUFU.EX2 (flush-to-zero; __expf adds a denormal-range fix-up of ~6 instructions per call)
+__device__ __forceinline__ float exp_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 __device__ __forceinline__ float act_fast(float x, int act) {
-    if (act == SPGNN_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
-    if (act == SPGNN_ACT_TANH) return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
+    if (act == SPGNN_ACT_ELU) return x > 0.f ? x : exp_fast(x) - 1.f;
+    if (act == SPGNN_ACT_TANH) return 1.f - __fdividef(2.f, exp_fast(2.f * x) + 1.f);
     if (act == SPGNN_ACT_RELU) return fmaxf(x, 0.f);
     return x;
 }
@@ -94,6 +100,20 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
+}
+// 64 mask bits for one 4-column chunk of a feat_drop mask (16 bits per element): two murmur3-style 32-bit
+// finalisers over (seed, chunk index) — 32-bit multiplies only, a third of the instructions of mix64 on the
+// bandwidth-bound plane producers.  Every producer / consumer of a planes dropout mask uses this one function.
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    return h ^ (h >> 16);
+}
+__host__ __device__ __forceinline__ uint64_t chunk_hash(uint64_t seed, uint64_t idx) {
+    const uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
+    const uint32_t a = fmix32(((uint32_t)seed ^ (lo * 0x9E3779B1u)) + hi * 0x85EBCA77u);
+    const uint32_t b = fmix32(((uint32_t)(seed >> 32) ^ (lo * 0xC2B2AE3Du) ^ a) + hi * 0x27D4EB2Fu);
+    return (uint64_t)a | ((uint64_t)b << 32);
 }
 __host__ __device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
     uint64_t h = mix64(seed ^ mix64(idx));

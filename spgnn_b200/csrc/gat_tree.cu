@@ -39,6 +39,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// explicit shared-space accesses with 32-bit addresses (pointers carved out of the dynamic shared array lose their
+// address space and would compile to generic LD/ST with 64-bit address arithmetic)
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct TArgs {
     Args a;
     const int64_t* node_off; int64_t B;
@@ -115,6 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_
             issue_slice(&zmap, smem_u32(&st.full[1]), zs_u32 + stage_bytes, nxt.n0, nxt.n, nxt.s * kCS);
     }
     float4 r[kPer];              // residual rows of the item about to be computed (prefetched one slice ahead)
+    float4 bv = a.bias ? ldg4(a.bias + l8 * 4) : zero4();
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         const int i = qw + k * kQW;
@@ -162,34 +174,36 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_
         float4 rc[kPer];
 #pragma unroll
         for (int k = 0; k < kPer; ++k) rc[k] = r[k];
+        const float4 bvc = bv;
         Cursor nn = cur;
         nn.advance(t);
         if (nn.valid(t)) {
+            const float* yrow = a.Y + (nn.n0 + qw) * a.ldy + a.res_off + nn.s * kCS + l8 * 4;
+            if (a.bias) bv = ldg4(a.bias + nn.s * kCS + l8 * 4);
 #pragma unroll
             for (int k = 0; k < kPer; ++k) {
                 const int i = qw + k * kQW;
-                r[k] = (has_res && i < nn.n) ? ldg4(a.Y + (nn.n0 + i) * a.ldy + a.res_off + nn.s * kCS + l8 * 4) : zero4();
+                r[k] = (has_res && i < nn.n) ? ldg4(yrow + (int64_t)(k * kQW) * a.ldy) : zero4();
             }
         }
         if (t.nstages == 1 && item > 0 && threadIdx.x == 0)
             issue_slice(&zmap, smem_u32(&st.full[0]), zs_u32, n0, n, s * kCS);
         mbar_wait(smem_u32(&st.full[stg]), par);
         // ---------------- phase B: one quarter-warp per node, 32 columns of head h
-        const float* zs = st.zs + (size_t)stg * t.nmax * kCS + l8 * 4;
+        const uint32_t zs = zs_u32 + stg * stage_bytes + l8 * 16;
         const int c = s * kCS + l8 * 4;                       // column inside [0, H*F)
         const int h = (s * kCS) / F;
-        const float4 bv = a.bias ? ldg4(a.bias + c) : zero4();
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
             const int i = qw + k * kQW;
             if (i < n) {
                 const short4s nb = st.nb[i];
                 const float4 w = *reinterpret_cast<const float4*>(st.w + (i * H + h) * 4);
-                float4 acc = add4(rc[k], bv);
-                acc = fma4(w.x, *reinterpret_cast<const float4*>(zs + nb.x * kCS), acc);
-                acc = fma4(w.y, *reinterpret_cast<const float4*>(zs + nb.y * kCS), acc);
-                acc = fma4(w.z, *reinterpret_cast<const float4*>(zs + nb.z * kCS), acc);
-                acc = fma4(w.w, *reinterpret_cast<const float4*>(zs + nb.w * kCS), acc);
+                float4 acc = add4(rc[k], bvc);
+                acc = fma4(w.x, lds4(zs + nb.x * (kCS * 4)), acc);
+                acc = fma4(w.y, lds4(zs + nb.y * (kCS * 4)), acc);
+                acc = fma4(w.z, lds4(zs + nb.z * (kCS * 4)), acc);
+                acc = fma4(w.w, lds4(zs + nb.w * (kCS * 4)), acc);
                 emit(a, n0 + i, c, act4(acc, a.act));
             }
         }
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
     const BSmem st = carve_b(smem, t.nmax, H, HF, t.nstages);
     const int l8 = threadIdx.x & 7, qw = threadIdx.x >> 3;
     const unsigned qmask = 0xFFu << (threadIdx.x & 24);
-    const uint32_t zs_u32 = smem_u32(st.zs);
+    const uint32_t zs_u32 = smem_u32(st.zs), gs_u32 = smem_u32(st.gs);
     const uint32_t stage_bytes = (uint32_t)t.nmax * kCS * 4;
     const bool has_res = a.res_mode == 1;
 
@@ -275,7 +289,9 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
     }
     // own-row operands of the item about to be computed: residual projection and the raw gradient sources
     float4 r[kPer], g[NG][kPer];
+    float4 bv = zero4();
     auto load_own = [&](const Cursor& it) {
+        if (a.bias) bv = ldg4(a.bias + it.s * kCS + l8 * 4);
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
             const int i = qw + k * kQW;
@@ -335,11 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
             issue_slice(&zmap, smem_u32(&st.full[0]), zs_u32, n0, n, s * kCS);
         mbar_wait(smem_u32(&st.full[stg]), par);
         // ---------------- dst side: g = g_out * act'(y) (y recomputed), G -> smem (+ dY residual part), <g, z_j>
-        const float* zs = st.zs + (size_t)stg * t.nmax * kCS + l8 * 4;
-        float* gsm = st.gs + l8 * 4;
+        const uint32_t zs = zs_u32 + stg * stage_bytes + l8 * 16;
+        const uint32_t gsm = gs_u32 + l8 * 16;
         const int c = s * kCS + l8 * 4;
         const int h = (s * kCS) / F;
-        const float4 bv = a.bias ? ldg4(a.bias + c) : zero4();
         float4 bsum = zero4();
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
@@ -348,10 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
                 const int64_t v = n0 + i;
                 const short4s nb = st.nb[i];
                 const float4 w = *reinterpret_cast<const float4*>(st.w + (i * H + h) * 4);
-                const float4 z0 = *reinterpret_cast<const float4*>(zs + nb.x * kCS);
-                const float4 z1 = *reinterpret_cast<const float4*>(zs + nb.y * kCS);
-                const float4 z2 = *reinterpret_cast<const float4*>(zs + nb.z * kCS);
-                const float4 z3 = *reinterpret_cast<const float4*>(zs + nb.w * kCS);
+                const float4 z0 = lds4(zs + nb.x * (kCS * 4)), z1 = lds4(zs + nb.y * (kCS * 4));
+                const float4 z2 = lds4(zs + nb.z * (kCS * 4)), z3 = lds4(zs + nb.w * (kCS * 4));
                 float4 acc = add4(r[k], bv);
                 acc = fma4(w.x, z0, acc); acc = fma4(w.y, z1, acc); acc = fma4(w.z, z2, acc); acc = fma4(w.w, z3, acc);
                 float4 go = zero4();
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
                                         (uint64_t)v * (uint64_t)gq_.nch + (uint64_t)(gq_.ch_off + (c >> 2))));
                 }
                 const float4 gq = mul4(go, actgrad4(act4(acc, a.act), a.act));
-                *reinterpret_cast<float4*>(gsm + i * kCS) = gq;
+                sts4(gsm + i * (kCS * 4), gq);
                 if (has_res) store_planes4(a.dY + v * a.dld + a.res_off + c, a.dps, gq);
                 bsum = add4(bsum, gq);
                 float d0 = dot4(gq, z0), d1 = dot4(gq, z1), d2 = dot4(gq, z2), d3 = dot4(gq, z3);
@@ -402,10 +415,10 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
             if (i < n) {
                 const short4s nb = st.onb[i];
                 const float4 w = *reinterpret_cast<const float4*>(st.ow + (i * H + h) * 4);
-                float4 acc = scale4(w.x, *reinterpret_cast<const float4*>(gsm + nb.x * kCS));
-                acc = fma4(w.y, *reinterpret_cast<const float4*>(gsm + nb.y * kCS), acc);
-                acc = fma4(w.z, *reinterpret_cast<const float4*>(gsm + nb.z * kCS), acc);
-                acc = fma4(w.w, *reinterpret_cast<const float4*>(gsm + nb.w * kCS), acc);
+                float4 acc = scale4(w.x, lds4(gsm + nb.x * (kCS * 4)));
+                acc = fma4(w.y, lds4(gsm + nb.y * (kCS * 4)), acc);
+                acc = fma4(w.z, lds4(gsm + nb.z * (kCS * 4)), acc);
+                acc = fma4(w.w, lds4(gsm + nb.w * (kCS * 4)), acc);
                 store_planes4(a.dY + (n0 + i) * a.dld + c, a.dps, acc);
             }
         }

@@ -686,7 +686,6 @@ __global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------- plane producers
-__device__ __forceinline__ uint64_t chunk_hash(uint64_t seed, uint64_t idx) { return mix64(seed ^ (idx * 0xD1B54A32D192ED03ull)); }
 
 // out planes [M, ldo] <- dropout([x1 | x2]) (scaled by 1/(1-p)); one thread per 4-column chunk of the concatenation.
 // Mask: 16 hash bits per element, chunk index = row * nchunks + chunk (the convention of every plane producer).

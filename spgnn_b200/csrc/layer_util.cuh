@@ -27,7 +27,6 @@ __device__ __forceinline__ float4 actgrad4(float4 y, int act) {
                        act_grad_from_out(y.z, act, 0.f), act_grad_from_out(y.w, act, 0.f));
 }
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : slope * x; }
-__device__ __forceinline__ uint64_t chunk_hash(uint64_t seed, uint64_t idx) { return mix64(seed ^ (idx * 0xD1B54A32D192ED03ull)); }
 
 // feat_drop of a consumer on a 4-column chunk (16 hash bits per element; same convention as spgnn_split_planes)
 __device__ __forceinline__ float4 drop4(float4 v, uint32_t thr, float scale, uint64_t seed, uint64_t chunk_idx) {
