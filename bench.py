@@ -36,6 +36,27 @@ LR, MOMENTUM = 5e-4, 0.9                               # train.py:14 default lr;
 SEED = 1234
 
 
+# C-ABI call -> its dominant kernel in the ncu capture (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py)
+NCU_KERNEL = {"planes_linear_bwd_weight": "tn_planes_kernel", "planes_linear_fwd": "nt_planes_kernel",
+              "planes_linear_bwd_input": "nt_planes_kernel", "wide_linear": "wide_kernel",
+              "gat_layer_fwd": "gat_tree_fwd_kernel", "gat_layer_bwd": "gat_tree_bwd_kernel",
+              "gat_aggx_fwd": "aggx_fwd_kernel", "split_planes": "split_planes_kernel"}
+
+
+def ncu_traffic(op, trees):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one training
+    step) of the kernel behind C-ABI call `op`, from the committed ncu --set full capture; None when there is no
+    capture at this batch size."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    k = d.get("kernels", {}).get(NCU_KERNEL.get(op, ""))
+    if not k or d.get("trees") != trees:
+        return None
+    return k["dram_bytes_per_launch"]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -208,6 +229,23 @@ def run_ours(args):
     ms = float(t.item())
     loss_val = float(loss.item())
 
+    # -------- inference (the metric's "infer" half): eval-mode forward + per-tree decision, no collectives
+    net.eval()
+    for _ in range(2):
+        runner.infer(net, g)
+    barrier()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(args.steps):
+        runner.infer(net, g)
+    i1.record()
+    barrier()
+    t = torch.tensor([i0.elapsed_time(i1) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    infer_ms = float(t.item())
+    net.train()
+
     # -------- per-kernel profile pass (CUDA events around every C-ABI call; separate from the timed region)
     roof, roof_agg, shares = None, None, None
     if rank == 0:
@@ -235,12 +273,14 @@ def run_ours(args):
             if d["flops"] > 0:
                 ach = d["flops"] / sec / 1e12
                 return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                        "frac": ach / pk["tf_sust"], "traffic": None, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
+                        "frac": ach / pk["tf_sust"], "traffic": ncu_traffic(name, B), "launches": d["n"],
+                        "avg_ms": d["ms"] / d["n"],
                         "peak_source": pk["src"] + " bf16 dense, sustained", "share_of_step": d["ms"] / total,
                         "note": "fp32-accurate projection; algorithmic flops 2*M*N*K"}
             ach = d["bytes"] / sec / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": ach / pk["hbm"], "traffic": None, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
+                    "frac": ach / pk["hbm"], "traffic": ncu_traffic(name, B), "launches": d["n"],
+                    "avg_ms": d["ms"] / d["n"], "algorithmic_bytes_per_launch": d["bytes"] / d["n"],
                     "peak_source": pk["src"] + " copy bandwidth", "share_of_step": d["ms"] / total,
                     "frac_of_nominal_8TBs": ach / 8000.0}
         dominant = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]
@@ -291,6 +331,9 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "nodes_per_s": gps * N / B,
+            "infer": {"value": world * B / (infer_ms / 1e3), "unit": "graphs/s", "ms_per_step": infer_ms,
+                      "nodes_per_s": world * N / (infer_ms / 1e3),
+                      "what": "eval-mode forward (7 GATConv + head) + per-tree per-class arg-max, batch resident in HBM"},
             "config": {"workload": "st_pgat_spgnn_3 train step (fwd+bwd+SGD), synthetic bifurcating airway trees n=301",
                        "trees_per_gpu": B, "nodes_per_gpu": N, "edges_per_gpu": E, "parallelism": f"dp{world} by graph",
                        "l2": "inputs (5.2 GB/GPU) larger than L2, no flush needed", "gemm_mode": ops.GEMM_MODE,
@@ -311,7 +354,7 @@ def main():
     ap.add_argument("--trees", type=int, default=4096, help="trees per GPU per step (BASELINE config 2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-trees", type=int, default=64)
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gemm-mode", type=int, default=None)
