@@ -156,6 +156,10 @@ int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, int64_t psc
                                    const uint16_t* X2, int64_t ldx2, int64_t psx2, int64_t K2,
                                    float* dW, int64_t lddw, int64_t M, int64_t N,
                                    void* ws, int64_t ws_bytes, void* stream);
+/* The launch plan planes_linear_bwd_weight would use (host only, no device work; for tests and profiling):
+ * out[0..7] = {swap (1: the gradient dC is the M-side operand), np_tiles, nq_tiles, row splits, CTAs, rows per
+ * split, 64-column blocks on the M side, on the N side}.  Returns the number of ints written (8). */
+int64_t spgnn_planes_linear_bwd_weight_plan(int64_t M, int64_t N, int64_t K1, int64_t K2, int32_t* out, int64_t cap);
 
 /* out[n] = sum_m X[m, n]  (bias gradients).  ws: spgnn_colsum_ws(N) bytes. */
 int64_t spgnn_colsum_ws(int64_t N);

@@ -118,7 +118,9 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     worst = 0
     for shp in [(128, 64, 0, 16), (300, 64, 0, 48), (1000, 1024, 39, 130), (257, 39, 0, 258), (513, 100, 8, 22),
-                (5000, 1024, 40, 1028), (4096, 192, 0, 4100), (3001, 768, 0, 516), (70000, 128, 64, 4100)]:
+                (5000, 1024, 40, 1028), (4096, 192, 0, 4100), (3001, 768, 0, 516), (70000, 128, 64, 4100),
+                # >= 4 x 74 m-tiles: the 2-CTA cluster (multicast weight tile) path, odd m-tile counts included
+                (38001, 512, 256, 516), (40100, 1024, 39, 1028), (37889, 256, 0, 258), (38017, 39, 0, 514)]:
         worst = max(worst, check(*shp))
     print("worst", worst)
     if "--bench" in sys.argv:

@@ -40,6 +40,17 @@ constexpr int kStgBytes = kEpiWarps * 32 * kStgLd * 4;
 constexpr int kSmemLimit = 232448;             // 227 KB opt-in limit per CTA
 constexpr int kNtFixed = 1024 /*align*/ + 256 /*barriers*/ + kStgBytes;
 
+// explicit shared-space accesses with 32-bit addresses: a float* carved out of the dynamic shared array compiles to
+// generic LD.E / ST.E with 64-bit address arithmetic (ncu: the staging store was the top stall line of wide_kernel)
+__device__ __forceinline__ float4 ld_shared4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void st_shared4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 struct NtMaps { CUtensorMap a1, a2, b; };
 struct NtArgs {
     const float* bias; int act; float slope;
@@ -57,6 +68,12 @@ struct NtShared {
     uint32_t tmem_base;
 };
 
+// CL = 2: clusters of two CTAs work on two adjacent m-tiles of the SAME n-tile in lock step; each CTA fetches half of
+// the weight tile and multicasts it to both, so the B tile crosses the L2 -> SM fabric once per cluster.  The ncu
+// capture of the CL = 1 kernel (profiles/r01_ncu_full_step_79ms_*) shows the big projections bound by that fabric
+// (85 KB per k-block per SM against ~43 B/clk/SM), tensor pipe 65-76 % busy.  Stage s of BOTH CTAs is free once both
+// UMMA issuers have committed it (empty barriers count CL arrivals, commits are multicast).
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_constant__ NtMaps maps, const NtArgs g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -68,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(smem_u32(&sh->full[s]), 1);
-            mbar_init(smem_u32(&sh->empty[s]), 1);
+            mbar_init(smem_u32(&sh->empty[s]), CL);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&sh->tmem_full[b]), 1);
@@ -84,22 +101,27 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
     if (warp == kEpiWarps) tmem_alloc(smem_u32(&sh->tmem_base), 512);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // the peer's barriers exist before anything is multicast into them
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
 
-    const int64_t n_tiles = g.nt_m * g.nt_n;
+    // work items: (m-tile, n-tile) for CL = 1; (pair of m-tiles, n-tile) per cluster for CL = 2, this CTA takes
+    // m-tile 2 * pair + rank (a pair's second tile may lie beyond M: loads are zero-filled, nothing is stored)
+    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int64_t n_tiles = (CL > 1 ? (g.nt_m + CL - 1) / CL : g.nt_m) * g.nt_n;
+    const int64_t tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
     const int nkb = g.kb1 + g.kb2;
 
     if (warp < kEpiWarps) {
         // ===================================================== epilogue: TMEM -> registers -> smem staging -> global
         int it = 0;
-        float* stg = reinterpret_cast<float*>(smem + stages_bytes + 256) + warp * (32 * kStgLd);
+        const uint32_t stg = smem_base + stages_bytes + 256 + warp * (32 * kStgLd * 4);
         const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
         const bool plain = (g.act == SPGNN_ACT_NONE) && (g.bias == nullptr);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
             const int buf = it & 1;
             const uint32_t par = (it >> 1) & 1;
-            const int64_t m0 = (tile / g.nt_n) * BM;
+            const int64_t m0 = ((tile / g.nt_n) * CL + rank) * BM;
             const int n0 = (int)(tile % g.nt_n) * g.BN;
             const int ncols = min(g.BN, g.N - n0);
             mbar_wait(smem_u32(&sh->tmem_full[buf]), par);
@@ -112,9 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * kStgLd + 4 * j) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    st_shared4(stg + (lane * kStgLd + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
                 const int cc = (lane & 7) * 4;
                 const int col = n0 + c0 + cc;
@@ -123,11 +143,11 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                 float* q = g.C + row0 * g.ldc + col;
                 const int64_t qstep = 4 * g.ldc;
                 const int nrow = (int)max((int64_t)0, min((int64_t)8, (g.M - row0 + 3) / 4));
-                const float* sp = stg + rsub * kStgLd + cc;
+                const uint32_t sp = stg + (rsub * kStgLd + cc) * 4;
                 if (plain && vec_ok && c0 + 32 <= ncols) {
 #pragma unroll
                     for (int itr = 0; itr < 8; ++itr)
-                        if (itr < nrow) st4(q + itr * qstep, *reinterpret_cast<const float4*>(sp + itr * 4 * kStgLd));
+                        if (itr < nrow) st4(q + itr * qstep, ld_shared4(sp + itr * (4 * kStgLd * 4)));
                 } else {
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (g.bias) {
@@ -138,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                     }
                     const int nvalid = ncols - (c0 + cc);
                     for (int itr = 0; itr < nrow; ++itr) {
-                        float4 x = *reinterpret_cast<const float4*>(sp + itr * 4 * kStgLd);
+                        float4 x = ld_shared4(sp + itr * (4 * kStgLd * 4));
                         x.x = act_fwd(x.x + bv.x, g.act, g.slope);
                         x.y = act_fwd(x.y + bv.y, g.act, g.slope);
                         x.z = act_fwd(x.z + bv.z, g.act, g.slope);
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
         if (lane == 0) {
             int it = 0;
             uint32_t kcount = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
                 const int buf = it & 1;
                 const uint32_t par = (it >> 1) & 1;
                 const int n0 = (int)(tile % g.nt_n) * g.BN;
@@ -191,7 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                         umma_bf16(tmem_d, dah, dbl, idesc, 1);
                         umma_bf16(tmem_d, dal, dbh, idesc, 1);
                     }
-                    umma_commit(smem_u32(&sh->empty[s]));      // frees the smem stage when these UMMAs retire
+                    // frees the smem stage when these UMMAs retire (in both CTAs of a cluster)
+                    if (CL > 1) umma_commit_mc(smem_u32(&sh->empty[s]), (uint16_t)((1u << CL) - 1));
+                    else umma_commit(smem_u32(&sh->empty[s]));
                 }
                 umma_commit(smem_u32(&sh->tmem_full[buf]));    // accumulator complete -> epilogue
             }
@@ -200,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
         // ===================================================== TMA producer (one thread)
         uint32_t kcount = 0;
         const uint32_t tx = (uint32_t)g.stage_bytes;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int m0 = (int)((tile / g.nt_n) * BM);
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            const int m0 = (int)(((tile / g.nt_n) * CL + rank) * BM);
             const int n0 = (int)(tile % g.nt_n) * g.BN;
             for (int kb = 0; kb < nkb; ++kb, ++kcount) {
                 const int s = kcount % g.stages;
@@ -212,13 +234,23 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                 const uint32_t dst = smem_base + s * g.stage_bytes;
                 if (kb < g.kb1) tma_load_3d(dst, &maps.a1, bar, kb * BK, m0, 0);
                 else tma_load_3d(dst, &maps.a2, bar, (kb - g.kb1) * BK, m0, 0);
-                tma_load_3d(dst + kABytes, &maps.b, bar, kb * BK, n0, 0);
+                if (CL > 1) {
+                    // this CTA's half of the weight tile (rows [rank * BN/2, ...) of both planes) goes to both CTAs
+                    const int half = g.BN / CL;
+                    const uint32_t off = (uint32_t)(rank * half * 128);
+                    const uint16_t mask = (uint16_t)((1u << CL) - 1);
+                    tma_load_3d_mc(dst + kABytes + off, &maps.b, bar, kb * BK, n0 + rank * half, 0, mask);
+                    tma_load_3d_mc(dst + kABytes + g.BN * 128 + off, &maps.b, bar, kb * BK, n0 + rank * half, 1, mask);
+                } else {
+                    tma_load_3d(dst + kABytes, &maps.b, bar, kb * BK, n0, 0);
+                }
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still signal its barriers
     if (warp == kEpiWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -251,7 +283,7 @@ constexpr int kWideFixed = 1024 /*align*/ + 256 /*barriers*/ + kWideStgBytes;
 
 template <int ACT>
 __device__ __forceinline__ float wide_act(float x, int act) {
-    if (ACT == SPGNN_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+    if (ACT == SPGNN_ACT_ELU) return x > 0.f ? x : exp_fast(x) - 1.f;     // FMUL + MUFU.EX2 + FADD on the x <= 0 side
     if (ACT == SPGNN_ACT_NONE) return x;
     return act_fwd(x, act, 0.f);
 }
@@ -261,6 +293,13 @@ __device__ __forceinline__ float wide_act_grad(float y, int act) {
     if (ACT == SPGNN_ACT_NONE) return 1.f;
     return act_grad_from_out(y, act, 0.f);
 }
+// act(x) and act'(x) from the pre-activation in one go (ELU: one exponential serves both)
+template <int ACT>
+__device__ __forceinline__ float wide_act_grad_pre(float x, int act) {
+    if (ACT == SPGNN_ACT_ELU) return x > 0.f ? 1.f : exp_fast(x);
+    if (ACT == SPGNN_ACT_NONE) return 1.f;
+    return act_grad_from_out(act_fwd(x, act, 0.f), act, 0.f);
+}
 __device__ __forceinline__ void st_planes4(__nv_bfloat16* q, int64_t ps, float4 d) {
     uint32_t h0, l0, h1, l1;
     split2(d.x, d.y, h0, l0);
@@ -268,13 +307,14 @@ __device__ __forceinline__ void st_planes4(__nv_bfloat16* q, int64_t ps, float4 
     *reinterpret_cast<uint2*>(q) = make_uint2(h0, h1);
     *reinterpret_cast<uint2*>(q + ps) = make_uint2(l0, l1);
 }
-
 // Epilogue of one 128 x BN x H tile for one warp: 16-column chunks; TMEM (lane = row) -> swizzled smem tile ->
 // (row = lane/4 + 8i, 4 columns) per thread, so that global accesses are whole 32/64-byte row segments.  In mode 1
 // the incoming gradient of the warp's four chunks is loaded BEFORE waiting for the accumulator, so its DRAM latency
-// hides behind the MMAs of this tile.
-template <int ACT>
-__device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg, float* dbias_row, uint32_t taddr,
+// hides behind the MMAs of this tile.  The MMA work per output element is small here (K = 2 x 192), so the tile is
+// only hidden behind the tensor pipe if the epilogue stays near ~1 issue slot per element: MODE and ACT are template
+// parameters, the staging tile is addressed in the shared window, row pointers are hoisted out of the head loop.
+template <int ACT, int MODE>
+__device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, uint32_t stg, float* dbias_row, uint32_t taddr,
                                                    int64_t m0, int n0, int ncols, int warp, int lane,
                                                    uint32_t full_bar, uint32_t full_par) {
     const int quad = warp & 3, part = warp >> 2;
@@ -282,30 +322,37 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
     const float inv_h = 1.f / (float)g.H;
     const int64_t row0 = m0 + quad * 32 + r0;
     const int nrow = (int)max((int64_t)0, min((int64_t)4, (g.M - row0 + 7) / 8));
+    // staging addresses: this lane's TMEM row (write side) and the four rows it reads back
+    const uint32_t st_w = stg + lane * 64;
+    const int sw_w = (lane >> 1) & 3;
+    uint32_t st_r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 8 * i;
+        st_r[i] = stg + r * 64 + ((cq ^ ((r >> 1) & 3)) << 4);
+    }
+    const int colq = n0 + cq * 4;
     for (int cg = 0; cg < ncols; cg += 128) {
         float4 run[2][4];
-        // gradient of the warp's four chunks: every load is issued before the first use (16 independent 16-byte
-        // loads in flight per thread), then the optional further sources are added chunk by chunk
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int c0 = cg + q * 64 + part * 16;
-            const int col = n0 + c0 + cq * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 run[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.mode == 1 && i < nrow && c0 < ncols) run[q][i] = ldg4(g.g[0] + (row0 + 8 * i) * g.ldg[0] + col);
+                if (MODE == 1 && i < nrow && c0 < ncols)
+                    run[q][i] = ldg4(g.g[0] + (row0 + 8 * i) * g.ldg[0] + colq + c0);
             }
         }
-        if (g.mode == 1) {
+        if (MODE == 1) {
             for (int s = 1; s < g.n_g; ++s) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int c0 = cg + q * 64 + part * 16;
-                    const int col = n0 + c0 + cq * 4;
                     float4 t[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        t[i] = (i < nrow && c0 < ncols) ? ldg4(g.g[s] + (row0 + 8 * i) * g.ldg[s] + col)
+                        t[i] = (i < nrow && c0 < ncols) ? ldg4(g.g[s] + (row0 + 8 * i) * g.ldg[s] + colq + c0)
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -313,6 +360,12 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
                     }
                 }
             }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    run[q][i].x *= inv_h; run[q][i].y *= inv_h; run[q][i].z *= inv_h; run[q][i].w *= inv_h;
+                }
         }
         if (cg == 0) {
             mbar_wait(full_bar, full_par);
@@ -322,7 +375,9 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
         for (int q = 0; q < 2; ++q) {
             const int c0 = cg + q * 64 + part * 16;
             if (c0 >= ncols) break;
-            const int col = n0 + c0 + cq * 4;
+            const int col = colq + c0;
+            __nv_bfloat16* dp = MODE == 1 ? g.dpre + row0 * g.ldd + col : nullptr;
+            const int64_t dstep = 8 * g.ldd;
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
             for (int h = 0; h < g.H; ++h) {
@@ -330,33 +385,29 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    st_shared4(st_w + ((j ^ sw_w) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
                 if (h + 1 < g.H) tmem_ld16(taddr + (h + 1) * g.BN + c0, v);      // next head: in flight during the math
                 float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int r = r0 + 8 * i;
-                    float4 x = *reinterpret_cast<const float4*>(stg + r * 16 + ((cq ^ ((r >> 1) & 3)) << 2));
-                    x.x = wide_act<ACT>(x.x + bv.x, g.act);
-                    x.y = wide_act<ACT>(x.y + bv.y, g.act);
-                    x.z = wide_act<ACT>(x.z + bv.z, g.act);
-                    x.w = wide_act<ACT>(x.w + bv.w, g.act);
-                    if (g.mode == 0) {
-                        run[q][i].x += x.x; run[q][i].y += x.y; run[q][i].z += x.z; run[q][i].w += x.w;
+                    float4 x = ld_shared4(st_r[i]);
+                    if (MODE == 0) {
+                        run[q][i].x += wide_act<ACT>(x.x + bv.x, g.act);
+                        run[q][i].y += wide_act<ACT>(x.y + bv.y, g.act);
+                        run[q][i].z += wide_act<ACT>(x.z + bv.z, g.act);
+                        run[q][i].w += wide_act<ACT>(x.w + bv.w, g.act);
                     } else if (i < nrow) {
                         float4 d;
-                        d.x = run[q][i].x * inv_h * wide_act_grad<ACT>(x.x, g.act);
-                        d.y = run[q][i].y * inv_h * wide_act_grad<ACT>(x.y, g.act);
-                        d.z = run[q][i].z * inv_h * wide_act_grad<ACT>(x.z, g.act);
-                        d.w = run[q][i].w * inv_h * wide_act_grad<ACT>(x.w, g.act);
-                        st_planes4(g.dpre + (row0 + 8 * i) * g.ldd + h * g.F + col, g.psd, d);
+                        d.x = run[q][i].x * wide_act_grad_pre<ACT>(x.x + bv.x, g.act);
+                        d.y = run[q][i].y * wide_act_grad_pre<ACT>(x.y + bv.y, g.act);
+                        d.z = run[q][i].z * wide_act_grad_pre<ACT>(x.z + bv.z, g.act);
+                        d.w = run[q][i].w * wide_act_grad_pre<ACT>(x.w + bv.w, g.act);
+                        st_planes4(dp + i * dstep + h * g.F, g.psd, d);
                         bs.x += d.x; bs.y += d.y; bs.z += d.z; bs.w += d.w;
                     }
                 }
-                if (g.mode == 1 && dbias_row) {
+                if (MODE == 1 && dbias_row) {
 #pragma unroll
                     for (int o = 4; o < 32; o <<= 1) {
                         bs.x += __shfl_xor_sync(kFull, bs.x, o); bs.y += __shfl_xor_sync(kFull, bs.y, o);
@@ -369,15 +420,17 @@ __device__ __forceinline__ void wide_epilogue_tile(const WideArgs& g, float* stg
                 }
                 __syncwarp();
             }
-            if (g.mode == 0) {
+            if (MODE == 0) {
+                float* po = g.out ? g.out + row0 * g.ldo + col : nullptr;
+                __nv_bfloat16* pp = g.outp ? g.outp + row0 * g.ldp + col : nullptr;
+                const int64_t ostep = 8 * g.ldo, pstep = 8 * g.ldp;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (i < nrow) {
-                        const int64_t r = row0 + 8 * i;
                         const float4 y = make_float4(run[q][i].x * inv_h, run[q][i].y * inv_h, run[q][i].z * inv_h,
                                                      run[q][i].w * inv_h);
-                        if (g.out) st4(g.out + r * g.ldo + col, y);
-                        if (g.outp) st_planes4(g.outp + r * g.ldp + col, g.psp, y);
+                        if (po) st4(po + i * ostep, y);
+                        if (pp) st_planes4(pp + i * pstep, g.psp, y);
                     }
                 }
             }
@@ -421,7 +474,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
     if (warp < kWideEpiWarps) {
         // ===================================================== epilogue
         int it = 0;
-        float* stg = reinterpret_cast<float*>(smem + stages_bytes + 256) + warp * (32 * 16);
+        const uint32_t stg = smem_base + stages_bytes + 256 + warp * (32 * 16 * 4);
         float* dbias_row = g.dbias_ws ? g.dbias_ws + (int64_t)blockIdx.x * (g.H * g.F) : nullptr;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -431,9 +484,15 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
             const int ncols = min(g.BN, g.F - n0);
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * accw);
             const uint32_t fb = smem_u32(&sh->tmem_full[buf]);
-            if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
-            else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
-            else wide_epilogue_tile<-1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+            if (g.mode == 0) {
+                if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU, 0>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE, 0>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else wide_epilogue_tile<-1, 0>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+            } else {
+                if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU, 1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE, 1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else wide_epilogue_tile<-1, 1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+            }
             tc_fence_before();
             mbar_arrive(smem_u32(&sh->tmem_empty[buf]));
         }
@@ -768,7 +827,7 @@ static EncodeTiledFn encode_fn() {
 
 // planes [rows, cols] (ld elements between rows, ps elements between the hi and lo plane) -> 3-D map {cols, rows, 2}
 static int make_planes_map(CUtensorMap* m, const void* hi, int64_t rows, int64_t cols, int64_t ld, int64_t ps,
-                           int box_cols, int box_rows) {
+                           int box_cols, int box_rows, int box_planes = 2) {
     EncodeTiledFn fn = encode_fn();
     SPGNN_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
     SPGNN_REQUIRE(((uintptr_t)hi & 15) == 0 && (ld * 2) % 16 == 0 && (ps * 2) % 16 == 0 && rows > 0 && cols > 0,
@@ -776,7 +835,7 @@ static int make_planes_map(CUtensorMap* m, const void* hi, int64_t rows, int64_t
                   (long long)ld, (long long)ps);
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ps * 2};
-    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(hi), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -805,13 +864,31 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
                      int64_t lda2, int64_t ps2, int64_t K2, const __nv_bfloat16* Bhi, int64_t ldb, const float* bias,
                      int act, float slope, float* C, int64_t ldc, int64_t M, int64_t N, cudaStream_t st) {
     static bool attr = false;
+    static int max_clusters = 0;             // co-resident 2-CTA clusters (0: cluster launches unavailable)
     if (!attr) {
-        SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_planes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_planes_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        // opt-in: measured neutral on B200 (profiles/r01_gemm_check_cluster_vs_plain.txt) - the projections are
+        // limited by board power (sw_power_cap, SM clock 1.3-1.7 GHz under the 3-pass UMMA load), not by the fabric
+        const char* e = getenv("SPGNN_NT_CLUSTER");
+        if (e && atoi(e) == 2) {
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = kSmemLimit; cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, nt_planes_kernel<2>, &cfg) == cudaSuccess) max_clusters = n;
+            else (void)cudaGetLastError();
+        }
         attr = true;
     }
     NtMaps maps;
     NtArgs a{};
     pick_bn((int)N, &a.BN, &a.nt_n);
+    // clusters pay when several m-tiles share a weight tile that is worth a k-loop: not for skinny outputs
+    const bool cluster = max_clusters > 0 && ceil_div(M, BM) >= 4 * (int64_t)max_clusters && a.BN >= 64;
     int rc = make_planes_map(&maps.a1, A1, M, K1, lda1, ps1, BK, BM);
     if (rc) return rc;
     if (A2 && K2 > 0) {
@@ -820,7 +897,8 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
     } else {
         maps.a2 = maps.a1;
     }
-    rc = make_planes_map(&maps.b, Bhi, N, ldb, ldb, N * ldb, BK, a.BN);
+    rc = cluster ? make_planes_map(&maps.b, Bhi, N, ldb, ldb, N * ldb, BK, a.BN / 2, 1)
+                 : make_planes_map(&maps.b, Bhi, N, ldb, ldb, N * ldb, BK, a.BN);
     if (rc) return rc;
     a.bias = bias; a.act = act; a.slope = slope; a.C = C; a.ldc = ldc; a.M = M; a.N = (int)N;
     a.nt_m = ceil_div(M, BM);
@@ -829,9 +907,22 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
     a.stage_bytes = kABytes + a.BN * 256;
     a.stages = (kSmemLimit - kNtFixed) / a.stage_bytes;
     if (a.stages > kMaxStages) a.stages = kMaxStages;
+    if (cluster) {
+        const int64_t items = ceil_div(a.nt_m, 2) * a.nt_n;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)(2 * (items < max_clusters ? items : max_clusters)));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemLimit; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        SPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, nt_planes_kernel<2>, maps, a));
+        count_launch();
+        return SPGNN_OK;
+    }
     const int64_t tiles = a.nt_m * a.nt_n;
     const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-    nt_planes_kernel<<<grid, kThreads, kSmemLimit, st>>>(maps, a);
+    nt_planes_kernel<1><<<grid, kThreads, kSmemLimit, st>>>(maps, a);
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }
@@ -1005,26 +1096,79 @@ struct TnPlan {
     int npb, nqb, np_tiles, nq_tiles;
     int64_t splits, rows;
 };
-int blocks_of(int64_t c0, int64_t c1) { return (int)(ceil_div(c0, 64) + (c1 > 0 ? ceil_div(c1, 64) : 0)); }
-int64_t load_cost(int npb, int nqb) {
-    const int pt = (int)ceil_div(npb, 4), qt = (int)ceil_div(nqb, 4);
-    return (int64_t)qt * npb + (int64_t)pt * nqb;          // 64-column block loads per k-step, all tiles
+// 64-column blocks of up to two concatenated sources, with the valid columns of each block
+int blocks_of(int64_t c0, int64_t c1, int* valid) {
+    int n = 0;
+    for (int64_t c : {c0, c1})
+        for (int64_t o = 0; o < c; o += 64) valid[n++] = (int)(c - o < 64 ? c - o : 64);
+    return n;
 }
+// Cycles one CTA spends per 32-node stage on a tile of pc P blocks x qc Q blocks: the tensor pipe needs
+// 2 k-steps x 3 passes x nacc x n_mma / 2 cycles (tcgen05 floor: M = 128 costs N/2 cycles per k16, a half-filled second
+// accumulator costs as much as a full one), the TMA fill needs (pc + qc) x 8 KB at the ~42.6 B/clk/SM share of the L2
+// throughput cap (~6300 B/clk chip-wide).  Against profiles/r01_ncu_full_step_79ms_table.txt this reproduces the
+// measured launches within a few percent (gat0 dW 7.7 ms, output-layer dW 2.1 ms with P = X vs 1.9 ms with P = dC).
+double tn_tile_cost(const int* qvalid, int pc, int q0, int qc) {
+    const int nacc = pc > 2 ? 2 : 1;
+    const int n_mma = 64 * (qc - 1) + ((qvalid[q0 + qc - 1] + 15) & ~15);
+    const double mma = 3.0 * nacc * n_mma, load = (pc + qc) * 8192.0 / 42.6;
+    return (mma > load ? mma : load) + 60.0;
+}
+void tn_range(int nb, int tiles, int t, int& first, int& count) {
+    const int base = nb / tiles, rem = nb % tiles;
+    first = t * base + (t < rem ? t : rem);
+    count = base + (t < rem ? 1 : 0);
+}
+// Orientation by the cost model (which operand is the M side: an accumulator takes 128 of its columns whether they
+// are valid or not, the N side has a granularity of 16), tiles of up to 4 x 4 blocks, row ranges UNIFORM over the
+// tile pairs: CTAs that share P or Q blocks then walk the same rows at the same time and meet in L2.  Measured
+// (profiles/r01_gemm_check_cluster_vs_plain.txt): the orientation flip takes the output layer's dW from 5.5 to 4.4 ms;
+// finer tilings that the model rates ~6 % better (6 x 6 x 4 for gat0) measure the same or worse, so they are not used.
 TnPlan tn_plan(int64_t M, int64_t N, int64_t K1, int64_t K2) {
-    TnPlan t;
-    const int xb = blocks_of(K1, K2), yb = blocks_of(N, 0);
-    t.swap = load_cost(yb, xb) < load_cost(xb, yb);
-    t.npb = t.swap ? yb : xb;
-    t.nqb = t.swap ? xb : yb;
+    int xv[1024], yv[1024];
+    const bool small = K1 + K2 <= 64 * 500 && N <= 64 * 1000;
+    const int xb = small ? blocks_of(K1, K2, xv) : (int)(ceil_div(K1, 64) + ceil_div(K2, 64));
+    const int yb = small ? blocks_of(N, 0, yv) : (int)ceil_div(N, 64);
+    const int sms = sm_count();
+    const int64_t max_by_rows = ceil_div(M, 512);
+    TnPlan best{};
+    double best_t = -1.0;
+    for (int sw = 0; small && sw < 2; ++sw) {
+        const int npb = sw ? yb : xb, nqb = sw ? xb : yb;
+        const int* qv = sw ? xv : yv;
+        const int npt = (int)ceil_div(npb, 4), nqt = (int)ceil_div(nqb, 4);
+        const int tiles = npt * nqt;
+        if (tiles > sms) continue;
+        double cmax = 0.0;
+        for (int tp = 0; tp < npt; ++tp)
+            for (int tq = 0; tq < nqt; ++tq) {
+                int p0, pc, q0, qc;
+                tn_range(npb, npt, tp, p0, pc);
+                tn_range(nqb, nqt, tq, q0, qc);
+                const double c = tn_tile_cost(qv, pc, q0, qc);
+                cmax = c > cmax ? c : cmax;
+            }
+        int64_t want = sms / tiles;
+        if (want > max_by_rows) want = max_by_rows;
+        if (want < 1) want = 1;
+        const int64_t rows = ceil_div(ceil_div(M, want), T_BK) * T_BK;
+        const int64_t splits = ceil_div(M, rows);
+        const double t = cmax * (double)(rows / T_BK);
+        if (best_t < 0.0 || t < 0.97 * best_t) {          // P = X unless the flip is clearly better
+            best_t = t;
+            best.swap = sw != 0; best.npb = npb; best.nqb = nqb; best.np_tiles = npt; best.nq_tiles = nqt;
+            best.splits = splits; best.rows = rows;
+        }
+    }
+    if (best_t >= 0.0) return best;
+    // more tile pairs than SMs: one row range, CTAs queue on the hardware scheduler
+    TnPlan t{};
+    t.swap = false;
+    t.npb = xb; t.nqb = yb;
     t.np_tiles = (int)ceil_div(t.npb, 4);
     t.nq_tiles = (int)ceil_div(t.nqb, 4);
-    const int64_t tiles = (int64_t)t.np_tiles * t.nq_tiles;
-    int64_t want = sm_count() / tiles;
-    const int64_t max_by_rows = ceil_div(M, 512);
-    if (want > max_by_rows) want = max_by_rows;
-    if (want < 1) want = 1;
-    t.rows = ceil_div(ceil_div(M, want), T_BK) * T_BK;
-    t.splits = ceil_div(M, t.rows);
+    t.rows = ceil_div(M, T_BK) * T_BK;
+    t.splits = 1;
     return t;
 }
 }  // namespace
@@ -1032,6 +1176,18 @@ TnPlan tn_plan(int64_t M, int64_t N, int64_t K1, int64_t K2) {
 extern "C" int64_t spgnn_planes_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K1, int64_t K2) {
     const TnPlan t = tn_plan(M, N, K1, K2);
     return t.splits * N * (K1 + K2) * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int64_t spgnn_planes_linear_bwd_weight_plan(int64_t M, int64_t N, int64_t K1, int64_t K2, int32_t* out,
+                                                       int64_t cap) {
+    if (!out || cap < 8 || M <= 0 || N <= 0 || K1 <= 0 || K2 < 0) return 0;
+    const TnPlan t = tn_plan(M, N, K1, K2);
+    const int tiles = t.np_tiles * t.nq_tiles;
+    const int64_t work = (int64_t)tiles * t.splits;
+    const int32_t head[8] = {t.swap, t.np_tiles, t.nq_tiles, (int32_t)t.splits, (int32_t)work, (int32_t)t.rows, t.npb, t.nqb};
+    int64_t n = 0;
+    for (; n < 8 && n < cap; ++n) out[n] = head[n];
+    return n;
 }
 
 // dW[N, K1+K2] (lddw) = dC[M, N]^T * [X1 | X2][M, K1+K2], every operand in planes form

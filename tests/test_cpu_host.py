@@ -119,3 +119,29 @@ def test_settings_loader_and_name_mapping(tmp_path):
     assert p.MODEL["pos_enc_dim"] == 39 and p.SAMPLING_RATE == 0.15 and set(PRESETS) >= {"st_gat_3", "st_gat_6_nr"}
     cw = [p.CLASS_WEIGHTS[k] for k in sorted(p.CLASS_WEIGHTS.keys())][1:]
     assert len(cw) == 22 and cw[0] == 0.2 and set(cw[1:]) == {0.8}                     # job_runner.py:1867
+
+
+def test_weight_gradient_launch_plan_is_sane():
+    """Host-only planner of the dW GEMM (spgnn_planes_linear_bwd_weight_plan): every CTA fits one wave, the splits
+    cover all rows, and the gradient goes on the M side exactly where that saves half-empty accumulators."""
+    from spgnn_b200._lib import lib
+    L = lib()
+    M = 4096 * 301
+    shapes = {"gat0": (1028, 1024, 39), "gat1": (516, 512, 256), "gat2": (260, 256, 128), "pgnn0": (514, 39, 0),
+              "pgnn1": (258, 256, 0), "pgnn2": (130, 128, 0), "head": (22, 1024, 0), "gat_out_head": (1024, 192, 192)}
+    plans = {}
+    for name, (N, K1, K2) in shapes.items():
+        out = (ctypes.c_int32 * 8)()
+        assert L.planes_linear_bwd_weight_plan(M, N, K1, K2, out, 8) == 8
+        swap, npt, nqt, splits, ctas, rows, npb, nqb = list(out)
+        plans[name] = swap
+        assert 1 <= ctas <= 148 and ctas == npt * nqt * splits
+        assert rows % 32 == 0 and rows * splits >= M > rows * (splits - 1)
+        assert npt == -(-npb // 4) and nqt == -(-nqb // 4)
+        xb = -(-K1 // 64) + (-(-K2 // 64) if K2 else 0)
+        yb = -(-N // 64)
+        assert (npb, nqb) == ((yb, xb) if swap else (xb, yb))
+    # X = [Ax_h | x] is 3 + 3 blocks: on the M side it fills 1.5 accumulators per tile, dC (16 blocks) fills them all
+    assert plans["gat_out_head"] == 1 and plans["gat0"] == 0
+    small = (ctypes.c_int32 * 8)()
+    assert L.planes_linear_bwd_weight_plan(300, 48, 64, 0, small, 8) == 8 and small[3] == 1 and small[4] == 1
