@@ -247,12 +247,15 @@ def run_ours(args):
     net.train()
 
     # -------- per-kernel profile pass (CUDA events around every C-ABI call; separate from the timed region)
+    # Every rank takes these steps (a step holds two collectives: the CE sums and the gradient all-reduce); only rank
+    # 0 keeps the per-call events.
     roof, roof_agg, shares = None, None, None
     if rank == 0:
         L.profile = []
-        for _ in range(max(1, min(3, args.steps))):
-            step()
-        torch.cuda.synchronize()
+    for _ in range(max(1, min(3, args.steps))):
+        step()
+    barrier()
+    if rank == 0:
         prof, L.profile = L.profile, None
         agg = {}
         for name, key, a, b in prof:
@@ -343,6 +346,7 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()                      # rank 0 may still be timing the CPU baseline: leave together
         dist.destroy_process_group()
 
 
