@@ -565,9 +565,11 @@ def _backward(plan: StackPlan, graph, tape, packed, head, g_logits, g_outs, need
         d.dbias, d.dbias_ws = ptr(db), ptr(dbw)
         gw = sum(1 for _ in srcs) * L.width
         L_.gat_layer_bwd(ctypes.byref(d), stream(),
-                         _key=("bytes", 4.0 * N * (gw + hf * (2 if L.res_mode == 1 else 1) + 2 * L.H)   # g, z, res
-                               + 4.0 * N * (2 * hf + (hf if L.res_mode == 1 else 2 * hf) + 2 * L.H)     # G w+r, dz
-                               + 8.0 * (N + 1) + 12.0 * E))
+                         # reads: gradient sources, z (+ residual projection), el/er; writes: dY planes (4 bytes
+                         # per column: dz | G as the residual part | d el, d er) (+ G workspace without residual)
+                         _key=("bytes", 4.0 * N * (gw + hf * (2 if L.res_mode == 1 else 1) + 2 * L.H)
+                               + 4.0 * N * (L.ycols + (0 if L.res_mode == 1 else hf))
+                               + 8.0 * (N + 1) + 12.0 * E + 8.0 * E * L.H))
         d_bias[i] = db
         d_packed[i] = planes_linear_bwd_weight(dY, ins[0], ins[1] if len(ins) > 1 else None)
         # dX only over the leading inputs that are produced inside the stack
