@@ -319,7 +319,7 @@ def run_ours(args):
                "pipeline": "H2D of batch i+1 overlaps step i (copy stream); first batch's copy is inside the timed region"}
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:     # reported at N=1 only (at N>1 the ranks share the host cores)
         cores = os.cpu_count() or 1
         rate, dt, nodes = cpu_oracle_rate(args.cpu_trees, 2, 1, cores)
         cpu = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
