@@ -145,3 +145,14 @@ def test_weight_gradient_launch_plan_is_sane():
     assert plans["gat_out_head"] == 1 and plans["gat0"] == 0
     small = (ctypes.c_int32 * 8)()
     assert L.planes_linear_bwd_weight_plan(300, 48, 64, 0, small, 8) == 8 and small[3] == 1 and small[4] == 1
+
+
+def test_descriptor_structs_match_the_library_layout():
+    """The ctypes mirrors of spgnn_gat_layer / spgnn_gat_wide (stack.py) must have the size the C side compiled."""
+    from spgnn_b200 import stack
+    from spgnn_b200._lib import lib
+    assert int(lib().gat_layer_sizeof()) == ctypes.sizeof(stack._Layer)
+    assert int(lib().gat_wide_sizeof()) == ctypes.sizeof(stack._Wide)
+    stack._checked = False
+    stack._check_abi()
+    assert stack._checked
