@@ -28,12 +28,28 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MODEL = dict(out_ch=22, fv_dim=1024, num_hiddens=[256, 128, 64], node_embed_dim=1024, num_gat_layers=3, num_heads=2,
-             num_out_heads=2, feat_drop=0.1, attn_drop=0.1, negative_slope=0.2, pos_hiddens=[256, 128, 64],
-             num_pos_heads=1, pos_enc_dim=39)          # exp_settings/st_pgat_spgnn_3.py:85-116 (GNN keys)
-SAMPLING_RATE = 0.15                                   # st_pgat_spgnn_3.py:79
+HEADLINE = "st_pgat_spgnn_3"                           # BASELINE.json configs[1]; the other presets are extra lines
 LR, MOMENTUM = 5e-4, 0.9                               # train.py:14 default lr; st_pgat_spgnn_3.py:124-128
 SEED = 1234
+ORACLE_KIND = {"models.GATNet": "gat", "models.GCNNet": "gcn", "models.GINNet": "gin", "models.SAGENet": "sage",
+               "models.GATPositionSPGNNNet": "spgnn"}
+
+
+def workload(name):
+    """(model kwargs, oracle kind, dotted class name, SAMPLING_RATE) of an exp_settings preset."""
+    from spgnn_b200.settings import PRESETS
+    st = PRESETS[name]
+    model = dict(st["MODEL"])
+    method = model.pop("method")
+    return model, ORACLE_KIND[method], method, st["SAMPLING_RATE"]
+
+
+def metric_name(name):
+    return "spgnn3_train_graphs_per_s" if name == HEADLINE else f"{name}_train_graphs_per_s"
+
+
+def workload_text(name):
+    return f"{name} train step (fwd+bwd+SGD), synthetic bifurcating airway trees n=301"
 
 
 # C-ABI call -> its dominant kernel in the ncu capture (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py)
@@ -98,25 +114,28 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(trees, steps, warmup, threads):
-    """graphs/s of the CPU oracle on SPGNN-3 fwd+bwd+SGD over `trees` synthetic trees (same generator, same model)."""
+def cpu_oracle_rate(trees, steps, warmup, threads, name=HEADLINE):
+    """graphs/s of the CPU oracle on one train step (fwd+bwd+SGD) of preset `name` over `trees` synthetic trees
+    (same generator, same model)."""
     import numpy as np
     import torch
     from oracle import dgl_ops, models as om, pe as ope
     from spgnn_b200 import synth
     torch.set_num_threads(threads)
+    model, kind, _, rate = workload(name)
     scans = synth.make_scans(0, trees, seed=SEED)
     gs = []
     for s in scans:
         g = dgl_ops.graph_from_adj(s.adj)
         g.ndata["fvs"] = torch.from_numpy(s.fvs)
-        anc = ope.anchors_39(s.fvs_out, s.adj)
-        g.ndata["pos_enc"] = torch.from_numpy(ope.dist_pos_enc(s.adj, anc)[0])
+        if kind == "spgnn":
+            anc = ope.anchors_39(s.fvs_out, s.adj)
+            g.ndata["pos_enc"] = torch.from_numpy(ope.dist_pos_enc(s.adj, anc)[0])
         gs.append(g)
     bg = dgl_ops.batch(gs)
     y = torch.from_numpy(np.concatenate([s.labels for s in scans]))
     torch.manual_seed(0)
-    net = om.GNNNet("spgnn", MODEL)
+    net = om.GNNNet(kind, model)
     net.init_like_reference()
     net.train()
     opt = torch.optim.SGD(net.parameters(), lr=LR, momentum=MOMENTUM)
@@ -125,7 +144,7 @@ def cpu_oracle_rate(trees, steps, warmup, threads):
 
     def step():
         opt.zero_grad()
-        mask = (y != 0) | (torch.rand(y.numel(), generator=gen) < SAMPLING_RATE)
+        mask = (y != 0) | (torch.rand(y.numel(), generator=gen) < rate)
         out = net(bg)
         loss = om.cross_entropy_masked(out[0], y, mask, cw)
         loss.backward()
@@ -148,14 +167,13 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     trees = args.cpu_trees
-    rate, dt, nodes = cpu_oracle_rate(trees, max(1, args.steps), max(1, min(args.warmup, 2)), cores)
+    rate, dt, nodes = cpu_oracle_rate(trees, max(1, args.steps), max(1, min(args.warmup, 2)), cores, args.workload)
     line = {
-        "impl": "reference", "metric": "spgnn3_train_graphs_per_s", "value": rate, "unit": "graphs/s",
+        "impl": "reference", "metric": metric_name(args.workload), "value": rate, "unit": "graphs/s",
         "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)),
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "nodes_per_s": rate * nodes / trees,
-        "config": {"workload": "st_pgat_spgnn_3 train step (fwd+bwd+SGD), synthetic bifurcating airway trees n=301",
-                   "trees_per_step": trees, "nodes_per_step": nodes},
+        "config": {"workload": workload_text(args.workload), "trees_per_step": trees, "nodes_per_step": nodes},
         "cpu_baseline": {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
                          "sample": f"{trees} trees/step (bounded sample of the 4096-tree batch); oracle = PyTorch-CPU "
                                    f"restatement of the DGL-0.7 op sequence, torch threads = {cores}"},
@@ -187,11 +205,14 @@ def run_ours(args):
     # -------- synthetic batch on device (this rank's shard of the global batch), positional encoding on device
     batch = synth_device.make_batch(first_tree=rank * B, count=B, seed=SEED)
     g = batch.graph
-    spe.distance_pos_enc(g, pos_enc_dim=MODEL["pos_enc_dim"])
+    model, kind, method, rate = workload(args.workload)
+    pe_dim = model.get("pos_enc_dim", 0) if kind == "spgnn" else 0
+    if pe_dim:
+        spe.distance_pos_enc(g, pos_enc_dim=pe_dim)
     N, E = g.num_nodes, g.num_edges
 
     torch.manual_seed(0)
-    net = sm.GATPositionSPGNNNet(**MODEL).to(dev)
+    net = getattr(sm, method.split(".")[-1])(**model).to(dev)
     net.init()
     net.train()
     net.set_gcn_only()
@@ -200,7 +221,7 @@ def run_ours(args):
     ops.manual_seed(SEED)
 
     def step():
-        return runner.train_step(net, g, opt, cw, SAMPLING_RATE)
+        return runner.train_step(net, g, opt, cw, rate)
 
     def barrier():
         if world > 1:
@@ -221,7 +242,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (L.launch_count() - l0) // args.steps
+    launches = L.launch_count() - l0                     # this library's kernel launches inside the timed region
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -268,27 +289,37 @@ def run_ours(args):
         shares = {k: round(d["ms"] / total, 4) for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         pk = peaks()
 
+        def traffic(name):
+            return ncu_traffic(name, B) if args.workload == HEADLINE else None     # the capture is of the headline
+
         def roofline(name):
             d = agg.get(name)
             if not d or d["ms"] == 0:
                 return None
             sec = d["ms"] / 1e3
+            if d["flops"] == 0 and d["bytes"] == 0:
+                return {"kernel": name, "bound": None, "achieved": None, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
+                        "share_of_step": d["ms"] / total, "note": "no algorithmic-work figure registered for this call"}
             if d["flops"] > 0:
                 ach = d["flops"] / sec / 1e12
                 return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                        "frac": ach / pk["tf_sust"], "traffic": ncu_traffic(name, B), "launches": d["n"],
+                        "frac": ach / pk["tf_sust"], "traffic": traffic(name), "launches": d["n"],
                         "avg_ms": d["ms"] / d["n"],
                         "peak_source": pk["src"] + " bf16 dense, sustained", "share_of_step": d["ms"] / total,
                         "note": "fp32-accurate projection; algorithmic flops 2*M*N*K"}
             ach = d["bytes"] / sec / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": ach / pk["hbm"], "traffic": ncu_traffic(name, B), "launches": d["n"],
+                    "frac": ach / pk["hbm"], "traffic": traffic(name), "launches": d["n"],
                     "avg_ms": d["ms"] / d["n"], "algorithmic_bytes_per_launch": d["bytes"] / d["n"],
                     "peak_source": pk["src"] + " copy bandwidth", "share_of_step": d["ms"] / total,
                     "frac_of_nominal_8TBs": ach / 8000.0}
         dominant = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]
         roof = roofline(dominant)
-        roof_agg = {"fwd": roofline("gat_layer_fwd"), "bwd": roofline("gat_layer_bwd")}
+        agg_calls = {"gat": ("gat_layer_fwd", "gat_layer_bwd"), "spgnn": ("gat_layer_fwd", "gat_layer_bwd"),
+                     "gcn": ("spmm", None), "gin": ("spmm", None), "sage": ("sage_maxpool_fwd", "sage_maxpool_bwd")}[kind]
+        roof_agg = {"fwd": roofline(agg_calls[0]), "bwd": roofline(agg_calls[1]) if agg_calls[1] else None}
+        if agg_calls[1] is None and roof_agg["fwd"]:
+            roof_agg["fwd"]["note"] = "forward and backward (transposed graph) aggregations are the same call"
 
     # -------- end to end through the public API from pinned host buffers
     e2e = None
@@ -300,8 +331,8 @@ def run_ours(args):
         def e2e_run(n):
             # public API: DeviceBatchLoader copies batch i+1 from pinned host memory on a copy stream while step i
             # computes; EVERY step's inputs cross PCIe inside the timed region and every step's loss is read back.
-            for gg in runner.DeviceBatchLoader((hb for _ in range(n)), pos_enc_dim=MODEL["pos_enc_dim"], device=dev):
-                ls = runner.train_step(net, gg, opt, cw, SAMPLING_RATE)
+            for gg in runner.DeviceBatchLoader((hb for _ in range(n)), pos_enc_dim=pe_dim, device=dev):
+                ls = runner.train_step(net, gg, opt, cw, rate)
                 float(ls.item())                         # D2H read of the loss
                 del gg
 
@@ -321,28 +352,29 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:     # reported at N=1 only (at N>1 the ranks share the host cores)
         cores = os.cpu_count() or 1
-        rate, dt, nodes = cpu_oracle_rate(args.cpu_trees, 2, 1, cores)
-        cpu = {"value": rate, "unit": "graphs/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_trees} trees/step x 2 steps (+1 warm-up) of the same SPGNN-3 train step; oracle = "
+        crate, dt, nodes = cpu_oracle_rate(args.cpu_trees, 2, 1, cores, args.workload)
+        cpu = {"value": crate, "unit": "graphs/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_trees} trees/step x 2 steps (+1 warm-up) of the same {args.workload} train step; oracle = "
                          f"PyTorch-CPU restatement of the DGL-0.7 op sequence (DGL not installable), {cores} threads",
                "ms_per_step": dt * 1e3}
 
     if rank == 0:
         gps = world * B / (ms / 1e3)
         line = {
-            "metric": "spgnn3_train_graphs_per_s", "value": gps, "unit": "graphs/s", "n_gpus": world,
+            "metric": metric_name(args.workload), "value": gps, "unit": "graphs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "nodes_per_s": gps * N / B,
             "infer": {"value": world * B / (infer_ms / 1e3), "unit": "graphs/s", "ms_per_step": infer_ms,
                       "nodes_per_s": world * N / (infer_ms / 1e3),
                       "what": "eval-mode forward (7 GATConv + head) + per-tree per-class arg-max, batch resident in HBM"},
-            "config": {"workload": "st_pgat_spgnn_3 train step (fwd+bwd+SGD), synthetic bifurcating airway trees n=301",
+            "config": {"workload": workload_text(args.workload),
                        "trees_per_gpu": B, "nodes_per_gpu": N, "edges_per_gpu": E, "parallelism": f"dp{world} by graph",
                        "l2": "inputs (5.2 GB/GPU) larger than L2, no flush needed", "gemm_mode": ops.GEMM_MODE,
                        "loss": loss_val},
             "roofline": roof, "roofline_agg": roof_agg, "kernel_time_shares": shares,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "gpu_launches_per_step": int(launches) // args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
@@ -357,6 +389,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--trees", type=int, default=4096, help="trees per GPU per step (BASELINE config 2)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=HEADLINE, help="exp_settings preset; the default is the headline "
+                    "(BASELINE.json configs[1]); st_gat_3|st_gat_6|st_gat_6_nr|st_gcn_3|st_gin_3|st_sage_3 give the "
+                    "extra lines of configs[2..3] (profiles/), never the driver's bench line")
     ap.add_argument("--cpu-trees", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")

@@ -134,7 +134,12 @@ class GIN(nn.Module):
         dims = [in_dim] + [num_hiddens[i] for i in range(num_layers)] + [out_ch]
         self.gin_layers = nn.ModuleList()
         for a, b in zip(dims[:-1], dims[1:]):
-            mlp = nn.Sequential(snn.Linear(a, b), snn.Dropout(0.1), snn.LeakyReLU(), snn.Linear(b, b), snn.LeakyReLU())
+            # models.py:358-383: Linear -> Dropout(0.1) -> LeakyReLU -> Linear -> LeakyReLU.  Both activations run in
+            # the projections' epilogues; LeakyReLU commutes with dropout (a non-negative per-element scale), so
+            # leaky(drop(lin(x))) == drop(leaky(lin(x))).  The placeholders keep the Sequential indices 0 and 3.
+            mlp = nn.Sequential(snn.Linear(a, b, act="leaky_relu", slope=0.01), snn.Dropout(0.1),
+                                snn.LeakyReLU(fused=True), snn.Linear(b, b, act="leaky_relu", slope=0.01),
+                                snn.LeakyReLU(fused=True))
             self.gin_layers.append(snn.GINConv(mlp, "mean", learn_eps=True))
 
     def forward(self, g, h=None):

@@ -39,12 +39,15 @@ class Dropout(nn.Module):
 
 
 class LeakyReLU(nn.Module):
-    def __init__(self, negative_slope=0.01):
+    """``fused=True``: a placeholder that keeps the reference's ``nn.Sequential`` indices (state-dict keys) while the
+    activation itself runs in the epilogue of the preceding :class:`Linear` (``act="leaky_relu"``)."""
+
+    def __init__(self, negative_slope=0.01, fused=False):
         super().__init__()
-        self.negative_slope = negative_slope
+        self.negative_slope, self.fused = negative_slope, fused
 
     def forward(self, x):
-        return ops.bias_act(x, None, "leaky_relu", self.negative_slope)
+        return x if self.fused else ops.bias_act(x, None, "leaky_relu", self.negative_slope)
 
 
 class GATConv(nn.Module):
@@ -118,7 +121,7 @@ class GATConv(nn.Module):
         xres = None
         if res_mode == 2:
             xres = feat if feat2 is None else ops.concat_dropout(feat, feat2, 0.0, False)
-        y = ops.LinearFn.apply(feat, feat2, self._packed_weight(), None, 0, 0.0)
+        y = ops.linear(feat, self._packed_weight(), x2=feat2)
         return ops.GatAggFn.apply(y, xres, self.bias, g, H, F, res_mode, self._act, self.negative_slope,
                                   bool(mean_heads), self.attn_drop_p if self.training else 0.0, ops.next_seed())
 

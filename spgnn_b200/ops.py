@@ -12,8 +12,10 @@ from ._lib import SpgnnError, lib, ptr, require_cuda, stream
 
 ACT = {None: 0, "none": 0, "elu": 1, "tanh": 2, "relu": 3, "leaky_relu": 4}
 
-# projection arithmetic: 0 = fp32 SIMT, 1 = tcgen05 split-bf16 tensor cores (see csrc/gemm_tc.cu)
-GEMM_MODE = 1
+# projection arithmetic of ``linear`` (GraphConv / SAGEConv / GINConv / nn.Linear; GAT stacks always take the planes
+# pipeline of stack.py): 0 = fp32 SIMT, 1 = tcgen05 split-bf16 with in-kernel conversion (csrc/gemm_tc.cu),
+# 2 = planes + TMA-fed tcgen05 (csrc/gemm_tma.cu)
+GEMM_MODE = 2
 
 _seed_state = {"seed": 0x5350474E, "counter": 0}
 
@@ -130,7 +132,75 @@ class LinearFn(Function):
         return dx1, dx2, dW, db, None, None
 
 
+def _planes_of(x):
+    """Planes of an fp32 activation, converted once per tensor: a tensor feeding several projections (SAGEConv's
+    ``h`` goes to fc_pool and fc_self) is split a single time.  The planes ride on the tensor object and are
+    dropped with it; an in-place update (version counter) invalidates them."""
+    from . import stack
+    c = getattr(x, "_spgnn_planes", None)
+    if c is not None and c[0] == x._version and c[1].buf.device == x.device:
+        return c[1]
+    P = stack.split_planes(x)
+    try:
+        x._spgnn_planes = (x._version, P)
+    except Exception:
+        pass
+    return P
+
+
+class PlanesLinearFn(Function):
+    """y = act([x1 | x2] @ W^T + bias) through the planes pipeline (GEMM_MODE 2): the inputs are converted to
+    split-bf16 planes once (``spgnn_split_planes``), the projection and both of its gradients are the TMA-fed
+    tcgen05 GEMMs of csrc/gemm_tma.cu, and the backward keeps the input PLANES (same bytes as the fp32 input)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, W, bias, act, slope):
+        from . import stack
+        require_cuda(x1, x2, W, bias)
+        W = _rows(W)
+        K1 = x1.shape[1]
+        K2 = x2.shape[1] if x2 is not None else 0
+        if W.shape[1] != K1 + K2:
+            raise SpgnnError(f"linear: weight has {W.shape[1]} columns, input has {K1}+{K2}")
+        P1 = _planes_of(x1)
+        P2 = _planes_of(x2) if x2 is not None else None
+        b = bias.contiguous() if bias is not None else None
+        y = stack.planes_linear(P1, W, b, act, float(slope), A2=P2)
+        need = ctx.needs_input_grad
+        ctx.planes = (P1, P2) if need[2] else None          # only the weight gradient reads the inputs again
+        ctx.save_for_backward(W, y if act else None)
+        ctx.cfg = (act, float(slope), bias is not None, K1, K2)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import stack
+        W, y = ctx.saved_tensors
+        act, slope, has_bias, K1, K2 = ctx.cfg
+        g = _rows(g)
+        M, N = g.shape
+        if act:
+            d = empty_padded(M, N, g.device)
+            lib().act_bwd(ptr(g), g.stride(0), ptr(y), y.stride(0), act, slope, ptr(d), d.stride(0), M, N, stream())
+            g = d
+        gp = stack.split_planes(g)
+        dx1 = dx2 = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx1 = stack.planes_linear_bwd_input(gp, W, K1, 0)
+        if K2 and ctx.needs_input_grad[1]:
+            dx2 = stack.planes_linear_bwd_input(gp, W, K2, K1)
+        if ctx.needs_input_grad[2]:
+            P1, P2 = ctx.planes
+            dW = stack.planes_linear_bwd_weight(gp, P1, P2)
+            ctx.planes = None
+        if has_bias and ctx.needs_input_grad[3]:
+            db = colsum(g)
+        return dx1, dx2, dW, db, None, None
+
+
 def linear(x1, W, bias=None, act=None, slope=0.0, x2=None):
+    if GEMM_MODE == 2:
+        return PlanesLinearFn.apply(x1, x2, W, bias, act_code(act), slope)
     return LinearFn.apply(x1, x2, W, bias, act_code(act), slope)
 
 
@@ -261,7 +331,8 @@ class SpmmFn(Function):
         out = empty_padded(N, F, x.device)
         b = bias.contiguous() if bias is not None else None
         lib().spmm(ptr(x), x.stride(0), ptr(graph.in_ptr), ptr(graph.in_src), ptr(pre), ptr(post), ptr(eps), ptr(b),
-                   act, float(slope), ptr(out), out.stride(0), N, F, stream())
+                   act, float(slope), ptr(out), out.stride(0), N, F, stream(),
+                   _key=("bytes", 8.0 * N * F + 4.0 * (N + 1) + 4.0 * graph.num_edges))
         ctx.save_for_backward(x if eps is not None else None, eps, out if act else None)
         ctx.graph, ctx.pre, ctx.post = graph, pre, post
         ctx.cfg = (act, float(slope), b is not None)
@@ -284,7 +355,8 @@ class SpmmFn(Function):
             dx = empty_padded(N, F, g.device)
             # transpose graph: out-edges, with the roles of the two norms swapped
             L.spmm(ptr(g), g.stride(0), ptr(gr.out_ptr), ptr(gr.out_dst), ptr(ctx.post), ptr(ctx.pre), ptr(eps), None,
-                   0, 0.0, ptr(dx), dx.stride(0), N, F, stream())
+                   0, 0.0, ptr(dx), dx.stride(0), N, F, stream(),
+                   _key=("bytes", 8.0 * N * F + 4.0 * (N + 1) + 4.0 * gr.num_edges))
         if eps is not None and ctx.needs_input_grad[1]:
             deps = (g * x).sum().reshape(1)
         if has_bias and ctx.needs_input_grad[2]:
@@ -303,7 +375,8 @@ class MaxPoolFn(Function):
         out = empty_padded(N, F, m.device)
         arg = torch.empty(N, F, dtype=torch.int32, device=m.device)
         lib().sage_maxpool_fwd(ptr(m), m.stride(0), ptr(graph.in_ptr), ptr(graph.in_src), ptr(out), out.stride(0),
-                               ptr(arg), N, F, stream())
+                               ptr(arg), N, F, stream(),
+                               _key=("bytes", 12.0 * N * F + 4.0 * (N + 1) + 4.0 * graph.num_edges))
         ctx.save_for_backward(arg)
         ctx.graph = graph
         return out
@@ -316,7 +389,8 @@ class MaxPoolFn(Function):
         N, F = g.shape
         dm = empty_padded(N, F, g.device)
         lib().sage_maxpool_bwd(ptr(g), g.stride(0), ptr(arg), ptr(gr.out_ptr), ptr(gr.out_dst), ptr(gr.out_slot),
-                               ptr(dm), dm.stride(0), N, F, stream())
+                               ptr(dm), dm.stride(0), N, F, stream(),
+                               _key=("bytes", 12.0 * N * F + 8.0 * (N + 1) + 8.0 * gr.num_edges))
         return dm, None
 
 

@@ -152,3 +152,56 @@ def test_training_step_at_4096_trees_is_reproducible(big):
     assert abs(losses[0][0] - losses[1][0]) <= 1e-6 * abs(losses[0][0])
     assert abs(losses[0][1] - losses[1][1]) <= 1e-5 * abs(losses[0][1])
     assert rel_err(params[0].cpu(), params[1].cpu()) < 1e-6
+
+
+NET_CLS = {"gat": "GATNet", "gcn": "GCNNet", "gin": "GINNet", "sage": "SAGENet"}
+
+
+@pytest.mark.parametrize("name", ["st_gat_3", "st_gat_6", "st_gat_6_nr", "st_gcn_3", "st_gin_3", "st_sage_3"])
+def test_other_presets_at_4096_trees(big, name):
+    """BASELINE.json configs[2..3] (GCN / GIN / SAGE aggregation kernels, the 6-layer GAT stacks) on the 4096-tree
+    ragged batch: rows of trees picked out of the big batch equal the same trees in a batch of their own and the
+    CPU oracle on those trees; one training step at full size gives a finite loss and moves the parameters."""
+    from oracle import dgl_ops, models as om
+    from spgnn_b200 import models as sm, ops, runner, synth, synth_device
+    kind, cfg = FULL_MODELS[name]
+    torch.manual_seed(1)
+    net = getattr(sm, NET_CLS[kind])(**cfg).cuda()
+    net.init()
+    net.eval()
+    g = big.graph
+    with torch.no_grad():
+        out = [o.detach() for o in net(g)]
+    assert out[0].shape == (g.num_nodes, 22) and torch.isfinite(out[0]).all()
+    off = g.node_off.cpu().numpy()
+    first, count = 3071, 2
+    rows = slice(off[first], off[first + count])
+    sb = synth_device.make_batch(first, count, ragged=True)
+    with torch.no_grad():
+        so = net(sb.graph)
+    for a, b in zip(so, out):
+        assert rel_err(a.cpu(), b[rows].cpu()) < 1e-6, name
+    scans = synth.make_scans(first, count, ragged=True)
+    onet = om.GNNNet(kind, cfg)
+    onet.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+    onet.eval()
+    gs = []
+    for i, s in enumerate(scans):
+        og = dgl_ops.graph_from_adj(s.adj)
+        og.ndata["fvs"] = g.ndata["fvs"][off[first + i]:off[first + i + 1]].cpu()
+        gs.append(og)
+    with torch.no_grad():
+        ref = onet(dgl_ops.batch(gs))
+    for a, r in zip(out, ref):
+        assert rel_err(a[rows].cpu(), r) < TOL, name
+    dec = ops.segmented_argmax(out[0], g).cpu().numpy()
+    assert ((dec >= off[:-1, None]) & (dec < off[1:, None])).all()
+    # one full-size training step
+    net.train()
+    net.set_gcn_only()
+    opt = runner.FlatSGD(net.parameters(), lr=5e-4, momentum=0.9)
+    before = opt.flat_p.clone()
+    cw = torch.tensor(runner.CLASS_WEIGHTS_22, device="cuda")
+    loss = float(runner.train_step(net, g, opt, cw, 0.15).item())
+    assert np.isfinite(loss) and loss > 0
+    assert torch.isfinite(opt.flat_p).all() and not torch.equal(opt.flat_p, before)

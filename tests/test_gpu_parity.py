@@ -102,12 +102,13 @@ def test_graph_errors(mods):
 
 
 # ------------------------------------------------------------------------------------------------ projection
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("M,K1,K2,N", [(300, 64, 0, 48), (1000, 1024, 39, 130), (257, 39, 0, 258), (513, 100, 7, 22),
                                        (128, 64, 0, 16), (5000, 1024, 40, 1028), (4096, 192, 0, 4100)])
 def test_linear_fwd_bwd_against_fp64(mods, M, K1, K2, N, mode, monkeypatch):
-    """mode 0: fp32 SIMT kernels; mode 1: tcgen05 split-bf16 tensor-core kernels (falls back per call when an
-    operand is not 16-byte aligned).  Both against an fp64 reference."""
+    """mode 0: fp32 SIMT kernels; mode 1: tcgen05 split-bf16 tensor-core kernels with in-kernel conversion (falls
+    back per call when an operand is not 16-byte aligned); mode 2 (the default): planes + TMA-fed tcgen05 GEMMs.
+    All against an fp64 reference."""
     ops = mods["ops"]
     monkeypatch.setattr(ops, "GEMM_MODE", mode)
     tol = 1e-5 if mode == 0 else 4e-5
@@ -166,8 +167,9 @@ def _margin_aware_flips(a, b, tol):
 def _full_cases():
     out = []
     for name in sorted(FULL_MODELS):
-        out.append((name, 1))                       # tensor-core projections (the default)
+        out.append((name, 2))                       # planes + TMA-fed tensor-core projections (the default)
         if FULL_MODELS[name][0] in ("gin", "sage", "gcn"):
+            out.append((name, 1))                   # tensor cores with in-kernel conversion
             out.append((name, 0))                   # fp32 SIMT projections
     return out
 
@@ -179,7 +181,7 @@ def test_full_width_forward_backward_vs_oracle(mods, name, mode, monkeypatch):
     GAT-family models are checked end to end with the tensor-core projections.  SAGE's max-pool and GIN's / SAGE's
     ReLU-type kinks make the GRADIENT a discontinuous function of the forward values: a 1e-6 perturbation of two
     nearly tied neighbours re-routes one sample's gradient (a ~1/sqrt(N) change of that weight row).  For those the
-    strict gradient bar is applied with the fp32 SIMT projections (mode 0), and with tensor cores (mode 1) the
+    strict gradient bar is applied with the fp32 SIMT projections (mode 0), and with tensor cores (modes 1, 2) the
     forward outputs keep the strict bar while gradients get a 3e-2 bar."""
     kind, cfg = FULL_MODELS[name]
     monkeypatch.setattr(mods["ops"], "GEMM_MODE", mode)
