@@ -270,10 +270,11 @@ def run_ours(args):
     # -------- per-kernel profile pass (CUDA events around every C-ABI call; separate from the timed region)
     # Every rank takes these steps (a step holds two collectives: the CE sums and the gradient all-reduce); only rank
     # 0 keeps the per-call events.
-    roof, roof_agg, shares = None, None, None
+    roof, roof_agg, shares, abi_ms = None, None, None, None
     if rank == 0:
         L.profile = []
-    for _ in range(max(1, min(3, args.steps))):
+    n_prof = max(1, min(3, args.steps))
+    for _ in range(n_prof):
         step()
     barrier()
     if rank == 0:
@@ -287,6 +288,7 @@ def run_ours(args):
                 d[key[0]] += key[1]
         total = sum(d["ms"] for d in agg.values())
         shares = {k: round(d["ms"] / total, 4) for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+        abi_ms = total / n_prof          # GPU time inside this library's calls per step (the rest is launch gaps)
         pk = peaks()
 
         def traffic(name):
@@ -372,7 +374,7 @@ def run_ours(args):
                        "trees_per_gpu": B, "nodes_per_gpu": N, "edges_per_gpu": E, "parallelism": f"dp{world} by graph",
                        "l2": "inputs (5.2 GB/GPU) larger than L2, no flush needed", "gemm_mode": ops.GEMM_MODE,
                        "loss": loss_val},
-            "roofline": roof, "roofline_agg": roof_agg, "kernel_time_shares": shares,
+            "roofline": roof, "roofline_agg": roof_agg, "kernel_time_shares": shares, "abi_ms_per_step": abi_ms,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "gpu_launches_per_step": int(launches) // args.steps, "clocks": clocks,
         }
@@ -393,7 +395,7 @@ def main():
                     "(BASELINE.json configs[1]); st_gat_3|st_gat_6|st_gat_6_nr|st_gcn_3|st_gin_3|st_sage_3 give the "
                     "extra lines of configs[2..3] (profiles/), never the driver's bench line")
     ap.add_argument("--cpu-trees", type=int, default=64)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gemm-mode", type=int, default=None)

@@ -166,6 +166,22 @@ int64_t spgnn_colsum_ws(int64_t N);
 int spgnn_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * GATConv weight packing.  One projection yields z, the residual projection (res_fc, models.py:301-314) and both
+ * attention logits when its weight is P = [W_fc ; W_res ; W_l ; W_r] with W_l[h, :] = sum_f attn_l[h, f] W_fc[hF+f, :]
+ * (el = (x W_fc^T).attn_l = x.(W_fc^T attn_l); DGL GATConv el/er).
+ *   pack_weight     : out [(HF * (1 + has W_res) + 2H), ldo] fp32, rows in the order above, columns [K, ldo) zeroed
+ *   pack_weight_bwd : gradient of P -> dW_fc [HF, lddw] (= dP rows + attn_l dP_l + attn_r dP_r), dW_res [HF, lddr],
+ *                     d attn_l / d attn_r [HF] (= <W_fc row, dP_l / dP_r of its head>); any output may be NULL.
+ * ---------------------------------------------------------------------------------- */
+int spgnn_gat_pack_weight(const float* W_fc, int64_t ldw, const float* W_res, int64_t ldr,
+                          const float* attn_l, const float* attn_r, int64_t H, int64_t F, int64_t K,
+                          float* out, int64_t ldo, void* stream);
+int spgnn_gat_pack_weight_bwd(const float* dP, int64_t ldp, const float* W_fc, int64_t ldw,
+                              const float* attn_l, const float* attn_r, int64_t H, int64_t F, int64_t K,
+                              int has_res, float* dW_fc, int64_t lddw, float* dW_res, int64_t lddr,
+                              float* d_attn_l, float* d_attn_r, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * GAT edge-softmax + aggregation + residual + bias + activation (+ head mean), fused.
  * Replaces DGL GATConv.forward K3-K9 as called at models.py:324,326,478,479,482,535,538.
  *   Y   [N, ldy]: cols [0,HF) z;  [res_off, res_off+HF) residual projection (res_mode 1);

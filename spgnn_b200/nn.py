@@ -95,17 +95,9 @@ class GATConv(nn.Module):
     def _packed_weight(self):
         """[W_fc ; W_res ; W_fc^T·attn_l ; W_fc^T·attn_r] with rows padded to 16 bytes: one projection yields
         z, the residual and both attention logits (el = x·(W_fc^T attn_l) ≡ (x W_fc^T)·attn_l)."""
-        H, F, K = self._num_heads, self._out_feats, self._in_feats
-        w = self.fc.weight
-        w3 = w.view(H, F, K)
-        wl = (w3 * self.attn_l.view(H, F, 1)).sum(1)
-        wr = (w3 * self.attn_r.view(H, F, 1)).sum(1)
-        blocks = [w] + ([self.res_fc.weight] if isinstance(self.res_fc, nn.Linear) else []) + [wl, wr]
-        wcat = torch.cat(blocks, 0)
-        kp = (K + 3) // 4 * 4
-        if kp != K:
-            wcat = torch.nn.functional.pad(wcat, (0, kp - K))[:, :K]
-        return wcat
+        w_res = self.res_fc.weight if isinstance(self.res_fc, nn.Linear) else None
+        return ops.PackWeightFn.apply(self.fc.weight, w_res, self.attn_l, self.attn_r, self._num_heads,
+                                      self._out_feats)
 
     def forward_flat(self, g, feat, feat2=None, mean_heads=False):
         if not self._allow_zero_in_degree:

@@ -266,6 +266,41 @@ def bias_act(x, bias=None, act=None, slope=0.0):
     return BiasActFn.apply(x, bias, act_code(act), slope)
 
 
+class PackWeightFn(Function):
+    """[W_fc ; W_res ; W_fc^T·attn_l ; W_fc^T·attn_r] of a GATConv in one kernel each way (include/spgnn_b200.h,
+    spgnn_gat_pack_weight).  Returns [rows, K] with 16-byte aligned rows."""
+
+    @staticmethod
+    def forward(ctx, w_fc, w_res, attn_l, attn_r, H, F):
+        require_cuda(w_fc, w_res, attn_l, attn_r)
+        w_fc = _rows(w_fc)
+        w_res = _rows(w_res) if w_res is not None else None
+        al, ar = attn_l.contiguous(), attn_r.contiguous()
+        K = w_fc.shape[1]
+        rows = H * F * (2 if w_res is not None else 1) + 2 * H
+        out = torch.empty(rows, _pad4(K), dtype=torch.float32, device=w_fc.device)
+        lib().gat_pack_weight(ptr(w_fc), w_fc.stride(0), ptr(w_res), w_res.stride(0) if w_res is not None else 0,
+                              ptr(al), ptr(ar), H, F, K, ptr(out), out.stride(0), stream())
+        ctx.save_for_backward(w_fc, al, ar)
+        ctx.cfg = (H, F, K, w_res is not None)
+        return out[:, :K]
+
+    @staticmethod
+    def backward(ctx, g):
+        w_fc, al, ar = ctx.saved_tensors
+        H, F, K, has_res = ctx.cfg
+        g = _rows(g)
+        need = ctx.needs_input_grad
+        dev = g.device
+        dW = torch.empty(H * F, K, dtype=torch.float32, device=dev) if need[0] else None
+        dR = torch.empty(H * F, K, dtype=torch.float32, device=dev) if (has_res and need[1]) else None
+        dal = torch.empty(al.shape, dtype=torch.float32, device=dev) if need[2] else None
+        dar = torch.empty(ar.shape, dtype=torch.float32, device=dev) if need[3] else None
+        lib().gat_pack_weight_bwd(ptr(g), g.stride(0), ptr(w_fc), w_fc.stride(0), ptr(al), ptr(ar), H, F, K,
+                                  int(has_res), ptr(dW), K, ptr(dR), K, ptr(dal), ptr(dar), stream())
+        return dW, dR, dal, dar, None, None
+
+
 class GatAggFn(Function):
     """Fused edge-softmax + aggregation + residual + bias + activation (+ head mean) over the projection output Y."""
 

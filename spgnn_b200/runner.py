@@ -17,8 +17,11 @@ CLASS_WEIGHTS_22 = [0.2] + [0.8] * 21      # exp_settings/st_pgat_spgnn_3.py:70-
 
 
 class FlatSGD:
-    """torch.optim.SGD(momentum) semantics over ONE flat fp32 bucket: parameters and gradients are views into two
-    contiguous buffers, so a step is one all-reduce (when world_size > 1) plus one fused update kernel."""
+    """torch.optim.SGD(momentum) semantics over ONE flat fp32 bucket: parameters are views into one contiguous
+    buffer and a step is one multi-tensor gather of the gradients into a second one, one all-reduce (when
+    world_size > 1) and one fused update kernel.  ``zero_grad`` drops the gradients (``p.grad = None``), so autograd
+    hands over each parameter's gradient without an accumulation kernel per parameter — at the reference's own batch
+    size (64 trees) a step is launch-bound and those ~40 tiny kernels are a tenth of it."""
 
     def __init__(self, params, lr, momentum=0.9, process_group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -30,20 +33,47 @@ class FlatSGD:
         self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.buf = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.g_views = []
         o = 0
         for p in self.params:
             k = p.numel()
             self.flat_p[o:o + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + k].view_as(p.data)
-            p.grad = self.flat_g[o:o + k].view_as(p.data)
+            self.g_views.append(self.flat_g[o:o + k].view_as(p.data))
+            p.grad = None
             o += k
         self.steps = 0
         self.numel = n
 
     def zero_grad(self):
-        self.flat_g.zero_()
+        for p in self.params:
+            p.grad = None
+
+    def _gather(self):
+        """p.grad of every parameter -> its slot of the flat bucket (one multi-tensor copy); parameters that got no
+        gradient contribute zeros.  Afterwards p.grad IS the slot, so callers see the (reduced) values."""
+        dst, src = [], []
+        missing = False
+        for p, v in zip(self.params, self.g_views):
+            g = p.grad
+            if g is None:
+                missing = True
+            elif g.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(g)
+        if missing:
+            self.flat_g.zero_()
+        if dst:
+            if hasattr(torch, "_foreach_copy_"):
+                torch._foreach_copy_(dst, src)
+            else:
+                for d, g in zip(dst, src):
+                    d.copy_(g)
+        for p, v in zip(self.params, self.g_views):
+            p.grad = v
 
     def step(self):
+        self._gather()
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
         lib().sgd_momentum(ptr(self.flat_p), ptr(self.flat_g), ptr(self.buf), self.numel, self.lr, self.momentum, 1.0,

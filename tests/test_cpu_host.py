@@ -156,3 +156,29 @@ def test_descriptor_structs_match_the_library_layout():
     stack._checked = False
     stack._check_abi()
     assert stack._checked
+
+
+def test_flat_sgd_gathers_gradients_into_one_bucket():
+    """FlatSGD host logic (no kernels): parameters become views of one buffer, gradients are gathered into the flat
+    bucket by one multi-tensor copy, parameters without a gradient contribute zeros, zero_grad drops gradients."""
+    import torch
+    from spgnn_b200.runner import FlatSGD
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2), torch.nn.Linear(7, 1))   # [2] is unused
+    before = [p.detach().clone() for p in net.parameters()]
+    opt = FlatSGD(net.parameters(), lr=0.1)
+    assert opt.numel == sum(b.numel() for b in before)
+    for p, b in zip(net.parameters(), before):
+        assert torch.equal(p.detach(), b) and p.grad is None
+        assert opt.flat_p.data_ptr() <= p.data_ptr() < opt.flat_p.data_ptr() + 4 * opt.numel
+    net[1](net[0](torch.randn(4, 5))).square().sum().backward()
+    ref = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in net.parameters()]
+    opt.flat_g.fill_(7.0)                                   # stale content must not survive
+    opt._gather()
+    assert torch.equal(opt.flat_g, torch.cat([r.reshape(-1) for r in ref]))
+    for p, v in zip(net.parameters(), opt.g_views):
+        assert p.grad.data_ptr() == v.data_ptr()
+    opt._gather()                                           # idempotent once p.grad is the slot
+    assert torch.equal(opt.flat_g, torch.cat([r.reshape(-1) for r in ref]))
+    opt.zero_grad()
+    assert all(p.grad is None for p in net.parameters())

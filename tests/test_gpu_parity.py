@@ -423,3 +423,31 @@ def test_device_synth_integer_part_is_bit_identical_to_host(mods):
             assert np.allclose(b.graph.ndata["fvs_out"][off[i]:off[i + 1]].cpu().numpy(), s.fvs_out, atol=1e-4)
         ref = mods["sg"].batch_from_adjs([s.adj for s in scans])
         assert torch.equal(ref.src, b.graph.src) and torch.equal(ref.dst, b.graph.dst)
+
+
+@pytest.mark.parametrize("H,F,K,res", [(2, 256, 1063, True), (1, 64, 39, True), (2, 1024, 192, True), (2, 64, 128, False),
+                                       (3, 20, 7, True)])
+def test_pack_weight_matches_the_torch_formula(mods, H, F, K, res):
+    """spgnn_gat_pack_weight (+bwd) vs [W_fc ; W_res ; (W_fc.view(H,F,K) * attn_l).sum(1) ; ... attn_r] in fp64."""
+    ops = mods["ops"]
+    gen = torch.Generator().manual_seed(H * 1000 + K)
+    w = torch.randn(H * F, K, generator=gen)
+    wr = torch.randn(H * F, K, generator=gen) if res else None
+    al, ar = torch.randn(1, H, F, generator=gen), torch.randn(1, H, F, generator=gen)
+    rows = H * F * (2 if res else 1) + 2 * H
+    go = torch.randn(rows, K, generator=gen)
+    leaves = [t.cuda().requires_grad_() if t is not None else None for t in (w, wr, al, ar)]
+    P = ops.PackWeightFn.apply(*leaves, H, F)
+    assert P.shape == (rows, K) and P.stride(0) % 4 == 0 and P.data_ptr() % 16 == 0
+    P.backward(go.cuda())
+    ref_leaves = [t.double().requires_grad_() if t is not None else None for t in (w, wr, al, ar)]
+    w3 = ref_leaves[0].view(H, F, K)
+    blocks = [ref_leaves[0]] + ([ref_leaves[1]] if res else []) + \
+        [(w3 * ref_leaves[2].view(H, F, 1)).sum(1), (w3 * ref_leaves[3].view(H, F, 1)).sum(1)]
+    Pr = torch.cat(blocks, 0)
+    Pr.backward(go.double())
+    assert rel_err(P.detach().cpu(), Pr.detach()) < 1e-6
+    for a, r in zip(leaves, ref_leaves):
+        if a is not None:
+            assert a.grad.shape == a.shape
+            assert rel_err(a.grad.cpu(), r.grad) < 1e-5
