@@ -29,6 +29,7 @@ constexpr int kBoxRows = 32;       // TMA box: 32 rows x 32 columns
 constexpr int kThreads = 512;
 constexpr int kQW = kThreads / 8;  // 64 quarter-warps; a quarter-warp owns one node of the slice (8 lanes x float4)
 constexpr int kPer = 6;            // nodes per quarter-warp per slice
+constexpr int kBatch = 3;          // rounds whose shared-memory gathers are issued together (kPer % kBatch == 0)
 constexpr int kMaxNodes = kQW * kPer;
 constexpr size_t kSmemLimit = 232448;
 
@@ -193,18 +194,32 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_
         const uint32_t zs = zs_u32 + stg * stage_bytes + l8 * 16;
         const int c = s * kCS + l8 * 4;                       // column inside [0, H*F)
         const int h = (s * kCS) / F;
+        // rounds kBatch at a time, out-of-range nodes clamped to node 0 (see the backward's source side)
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int i = qw + k * kQW;
-            if (i < n) {
-                const short4s nb = st.nb[i];
-                const float4 w = *reinterpret_cast<const float4*>(st.w + (i * H + h) * 4);
-                float4 acc = add4(rc[k], bvc);
-                acc = fma4(w.x, lds4(zs + nb.x * (kCS * 4)), acc);
-                acc = fma4(w.y, lds4(zs + nb.y * (kCS * 4)), acc);
-                acc = fma4(w.z, lds4(zs + nb.z * (kCS * 4)), acc);
-                acc = fma4(w.w, lds4(zs + nb.w * (kCS * 4)), acc);
-                emit(a, n0 + i, c, act4(acc, a.act));
+        for (int k0 = 0; k0 < kPer; k0 += kBatch) {
+            if ((qw & ~3) + k0 * kQW < n) {                    // warp-uniform
+                short4s nb[kBatch];
+                float4 w[kBatch], acc[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int i = qw + (k0 + j) * kQW;
+                    const int ii = i < n ? i : 0;
+                    nb[j] = st.nb[ii];
+                    w[j] = *reinterpret_cast<const float4*>(st.w + (ii * H + h) * 4);
+                }
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    acc[j] = add4(rc[k0 + j], bvc);
+                    acc[j] = fma4(w[j].x, lds4(zs + nb[j].x * (kCS * 4)), acc[j]);
+                    acc[j] = fma4(w[j].y, lds4(zs + nb[j].y * (kCS * 4)), acc[j]);
+                    acc[j] = fma4(w[j].z, lds4(zs + nb[j].z * (kCS * 4)), acc[j]);
+                    acc[j] = fma4(w[j].w, lds4(zs + nb[j].w * (kCS * 4)), acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int i = qw + (k0 + j) * kQW;
+                    if (i < n) emit(a, n0 + i, c, act4(acc[j], a.act));
+                }
             }
         }
         __syncthreads();
@@ -409,17 +424,34 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
             st.sb[s * kCS + threadIdx.x] += acc;
         }
         // ---------------- src side: dz[u] = sum over out-edges (u -> v) of a_drop * G[v]
+        // Rounds are taken kBatch at a time with the out-of-range nodes clamped to node 0 instead of branched around:
+        // the neighbour lists of the whole batch are read first, then all 4 * kBatch gathers are in flight together
+        // (the per-round chain list -> gather -> FMA -> store left the 4 warps of a scheduler waiting on shared-memory
+        // latency: 18 % of this kernel's stall samples sat on these lines, profiles/r01_ncu_tree_bwd_source.txt).
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int i = qw + k * kQW;
-            if (i < n) {
-                const short4s nb = st.onb[i];
-                const float4 w = *reinterpret_cast<const float4*>(st.ow + (i * H + h) * 4);
-                float4 acc = scale4(w.x, lds4(gsm + nb.x * (kCS * 4)));
-                acc = fma4(w.y, lds4(gsm + nb.y * (kCS * 4)), acc);
-                acc = fma4(w.z, lds4(gsm + nb.z * (kCS * 4)), acc);
-                acc = fma4(w.w, lds4(gsm + nb.w * (kCS * 4)), acc);
-                store_planes4(a.dY + (n0 + i) * a.dld + c, a.dps, acc);
+        for (int k0 = 0; k0 < kPer; k0 += kBatch) {
+            if ((qw & ~3) + k0 * kQW < n) {                    // warp-uniform: this warp has a node in round k0
+                short4s nb[kBatch];
+                float4 w[kBatch], acc[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int i = qw + (k0 + j) * kQW;
+                    const int ii = i < n ? i : 0;
+                    nb[j] = st.onb[ii];
+                    w[j] = *reinterpret_cast<const float4*>(st.ow + (ii * H + h) * 4);
+                }
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    acc[j] = scale4(w[j].x, lds4(gsm + nb[j].x * (kCS * 4)));
+                    acc[j] = fma4(w[j].y, lds4(gsm + nb[j].y * (kCS * 4)), acc[j]);
+                    acc[j] = fma4(w[j].z, lds4(gsm + nb[j].z * (kCS * 4)), acc[j]);
+                    acc[j] = fma4(w[j].w, lds4(gsm + nb[j].w * (kCS * 4)), acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j) {
+                    const int i = qw + (k0 + j) * kQW;
+                    if (i < n) store_planes4(a.dY + (n0 + i) * a.dld + c, a.dps, acc[j]);
+                }
             }
         }
         __syncthreads();
