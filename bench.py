@@ -48,8 +48,9 @@ def metric_name(name):
     return "spgnn3_train_graphs_per_s" if name == HEADLINE else f"{name}_train_graphs_per_s"
 
 
-def workload_text(name):
-    return f"{name} train step (fwd+bwd+SGD), synthetic bifurcating airway trees n=301"
+def workload_text(name, ragged=False):
+    return f"{name} train step (fwd+bwd+SGD), synthetic bifurcating airway trees " + \
+        ("n in [241, 361], mean 301" if ragged else "n=301")
 
 
 # C-ABI call -> its dominant kernel in the ncu capture (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py)
@@ -203,7 +204,7 @@ def run_ours(args):
     L = lib()
 
     # -------- synthetic batch on device (this rank's shard of the global batch), positional encoding on device
-    batch = synth_device.make_batch(first_tree=rank * B, count=B, seed=SEED)
+    batch = synth_device.make_batch(first_tree=rank * B, count=B, seed=SEED, ragged=args.ragged)
     g = batch.graph
     model, kind, method, rate = workload(args.workload)
     pe_dim = model.get("pos_enc_dim", 0) if kind == "spgnn" else 0
@@ -370,7 +371,7 @@ def run_ours(args):
             "infer": {"value": world * B / (infer_ms / 1e3), "unit": "graphs/s", "ms_per_step": infer_ms,
                       "nodes_per_s": world * N / (infer_ms / 1e3),
                       "what": "eval-mode forward (7 GATConv + head) + per-tree per-class arg-max, batch resident in HBM"},
-            "config": {"workload": workload_text(args.workload),
+            "config": {"workload": workload_text(args.workload, args.ragged),
                        "trees_per_gpu": B, "nodes_per_gpu": N, "edges_per_gpu": E, "parallelism": f"dp{world} by graph",
                        "l2": "inputs (5.2 GB/GPU) larger than L2, no flush needed", "gemm_mode": ops.GEMM_MODE,
                        "loss": loss_val},
@@ -396,6 +397,7 @@ def main():
                     "extra lines of configs[2..3] (profiles/), never the driver's bench line")
     ap.add_argument("--cpu-trees", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--ragged", action="store_true", help="tree sizes n in [241, 361] (mean 301) instead of n = 301")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gemm-mode", type=int, default=None)

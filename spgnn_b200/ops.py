@@ -179,12 +179,26 @@ class PlanesLinearFn(Function):
         act, slope, has_bias, K1, K2 = ctx.cfg
         g = _rows(g)
         M, N = g.shape
-        if act:
-            d = empty_padded(M, N, g.device)
-            lib().act_bwd(ptr(g), g.stride(0), ptr(y), y.stride(0), act, slope, ptr(d), d.stride(0), M, N, stream())
-            g = d
-        gp = stack.split_planes(g)
         dx1 = dx2 = dW = db = None
+        want_db = has_bias and ctx.needs_input_grad[3]
+        n4 = _pad4(N)
+        if (g.stride(0) % 4 == 0 and g.stride(0) >= n4 and g.data_ptr() % 16 == 0 and
+                (not act or (y.stride(0) % 4 == 0 and y.stride(0) >= n4 and y.data_ptr() % 16 == 0))):
+            # one pass: d = g * act'(y) -> planes (+ bias gradient)
+            L = lib()
+            gp = stack.Planes(M, N, g.device)
+            db = torch.empty(N, dtype=torch.float32, device=g.device) if want_db else None
+            ws = _ws(L.act_bwd_planes_ws(N), g.device) if want_db else None
+            L.act_bwd_planes(ptr(g), g.stride(0), ptr(y) if act else None, y.stride(0) if act else 0, act, slope,
+                             gp.ptr(), gp.ld, gp.ps, M, N, ptr(db), ptr(ws), stream(),
+                             _key=("bytes", (12.0 if act else 8.0) * M * N))
+            want_db = False
+        else:
+            if act:
+                d = empty_padded(M, N, g.device)
+                lib().act_bwd(ptr(g), g.stride(0), ptr(y), y.stride(0), act, slope, ptr(d), d.stride(0), M, N, stream())
+                g = d
+            gp = stack.split_planes(g)
         if ctx.needs_input_grad[0]:
             dx1 = stack.planes_linear_bwd_input(gp, W, K1, 0)
         if K2 and ctx.needs_input_grad[1]:
@@ -193,7 +207,7 @@ class PlanesLinearFn(Function):
             P1, P2 = ctx.planes
             dW = stack.planes_linear_bwd_weight(gp, P1, P2)
             ctx.planes = None
-        if has_bias and ctx.needs_input_grad[3]:
+        if want_db:
             db = colsum(g)
         return dx1, dx2, dW, db, None, None
 
