@@ -1,4 +1,4 @@
-"""Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv): per-kernel totals, and the last full step.
+"""Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv): per-kernel totals of one training step.
 
     python scripts/launch_summary.py gpurun_out/launches.csv [marker_kernel_substring]
 """
@@ -18,8 +18,12 @@ for r in rows[1:]:
 marker = sys.argv[2] if len(sys.argv) > 2 else "sgd_momentum"
 ends = [i for i, x in enumerate(L) if marker in x[0]]
 if len(ends) >= 2:
-    step = L[ends[-2] + 1: ends[-1] + 1]
-    print(f"last full step: launches {len(step)}, sum {sum(x[1] for x in step):.2f} ms")
+    # a training step = the launches between two optimiser updates; bench.py also runs inference passes between its
+    # timed steps and its profile step, so take the segment with the fewest launches (a pure training step)
+    segs = [L[a + 1: b + 1] for a, b in zip(ends[:-1], ends[1:])]
+    step = min(segs, key=len)
+    print(f"one training step: launches {len(step)}, sum {sum(x[1] for x in step):.2f} ms "
+          f"({len(ends)} optimiser updates in the capture)")
 else:
     step = L
 agg = collections.OrderedDict()
