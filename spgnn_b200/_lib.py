@@ -12,7 +12,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspgnn_b200.so")
+LIB_PATH = os.environ.get("SPGNN_B200_LIB") or os.path.join(_HERE, "libspgnn_b200.so")   # override: A/B of two builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "spgnn_b200.h")
 
 _CT = {
