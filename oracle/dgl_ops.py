@@ -270,6 +270,17 @@ class GraphConv(nn.Module):
         return rst
 
 
+class Block:
+    """Message-flow graph of DGL's neighbour sampling (``dgl.to_block``): edges ``src[i] -> dst[i]`` from ``num_src``
+    source rows to ``num_dst`` destination rows; destination node i is source node i."""
+
+    def __init__(self, src, dst, num_src, num_dst):
+        self.src = torch.as_tensor(src, dtype=torch.int64)
+        self.dst = torch.as_tensor(dst, dtype=torch.int64)
+        self.num_src, self.num_dst = int(num_src), int(num_dst)
+        self.srcdata, self.dstdata = {}, {}
+
+
 class SAGEConv(nn.Module):
     """aggregator_type='pool' only (models.py:660, 668-679)."""
 
@@ -297,9 +308,13 @@ class SAGEConv(nn.Module):
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
     def forward(self, g, feat):
-        n = g.num_nodes
         h = self.feat_drop(feat)
         m = F.relu(self.fc_pool(h))
+        if isinstance(g, Block):                   # DGL: feat_dst = feat_src[:number_of_dst_nodes()]
+            n = g.num_dst
+            h = h[:n]
+        else:
+            n = g.num_nodes
         neigh = _seg_max(m[g.src], g.dst, n)
         neigh = torch.where(torch.isinf(neigh), torch.zeros_like(neigh), neigh)   # DGL zero-fills empty rows
         rst = self.fc_self(h) + self.fc_neigh(neigh)

@@ -101,6 +101,13 @@ class SAGE(_Stack):
             h = layer(g, h)
         return h
 
+    def forward_batch(self, blocks, x):
+        # models.py:685-689
+        h = x
+        for layer, block in zip(self.g_layers, blocks):
+            h = layer(block, h)
+        return h
+
 
 class GATPSPGNN(_Stack):
     # models.py:403-484: structure stream consumes h_p BEFORE the position layer updates it (:476-479);
@@ -205,6 +212,11 @@ class GNNNet(nn.Module):
             self.stack.reset_parameters()
         nn.init.xavier_normal_(self.gnn_out.weight, gain=nn.init.calculate_gain("linear"))
         nn.init.constant_(self.gnn_out.bias, 0.0)
+
+    def forward_batch(self, blocks, x):
+        # SAGENet.forward_batch, models.py:814-817
+        n_embed = self.stack.forward_batch(blocks, x)
+        return self.gnn_out(n_embed), n_embed
 
     def forward(self, g):
         res = self.stack(g)

@@ -201,6 +201,40 @@ class GCNTrainSPGNN(GCNTrain):
     uses_pos_enc = True
 
 
+class GCNTrainSAGE(GCNTrain):
+    """GCNTrainSAGE.train (job_runner.py:1460-1514): every GCN step draws ``node_sample_rate`` of the batch's nodes,
+    walks them in mini-batches of NODE_BATCH_SIZE seeds through ``MultiLayerNeighborSampler(node_ks)`` blocks and
+    takes one optimiser step per mini-batch with the class-weighted CE over the seeds (no node mask here)."""
+
+    def train_batch(self, scans, steps=None, max_minibatches=None):
+        from . import sampling
+        s = self.settings
+        self.model.train()
+        g = self.to_device(scans)
+        sampler = sampling.MultiLayerNeighborSampler(self.model.sage.node_ks)
+        node_bs = int(getattr(s, "NODE_BATCH_SIZE", 64))
+        losses = []
+        for n in range(s.GCN_STEPS if steps is None else steps):
+            nids = random.sample(range(g.num_nodes), int(g.num_nodes * self.model.sage.node_sample_rate))
+            loader = sampling.NodeDataLoader(g, nids, sampler, device=self.device, batch_size=node_bs, shuffle=True,
+                                             drop_last=False)
+            loss = None
+            for k, (input_nodes, seeds, blocks) in enumerate(loader):
+                if max_minibatches is not None and k >= max_minibatches:
+                    break
+                self.optimizer.zero_grad()
+                out, _ = self.model.forward_batch(blocks, blocks[0].srcdata["fvs"])
+                loss = ops.masked_cross_entropy(out, blocks[-1].dstdata["y"], self.class_w, rate=1.0)
+                loss.backward()
+                self.optimizer.step()
+            if n % s.LOG_STEPS == 0 and loss is not None:
+                losses.append(float(loss.item()))
+                self.logger.info("Step %d-%d, LOSS: %.5f, LR:%.5f.", self.epoch_n, self.current_iteration, losses[-1],
+                                 self.optimizer.lr)
+            self.current_iteration += 1
+        return losses
+
+
 def branch_accuracy(decision, y):
     """Fraction of (tree, class 1..21) pairs whose arg-max node carries that label: the branch-level part of
     job_runner.py:158-165 + :878-893 (voxel-level relabelling is out of scope)."""

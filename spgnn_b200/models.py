@@ -169,8 +169,13 @@ class SAGE(_ConvStack):
         return h
 
     def forward_batch(self, blocks, x):
-        raise SpgnnError("neighbour-sampled mini-batches (dgl.dataloading blocks) are not implemented "
-                         "(SURVEY.md §8f rank 4); use full-graph forward(g)")
+        """models.py:685-689 on the blocks of ``sampling.MultiLayerNeighborSampler`` (one block per layer)."""
+        if len(blocks) != len(self.g_layers):
+            raise SpgnnError(f"SAGE.forward_batch: {len(self.g_layers)} layers need as many blocks, got {len(blocks)}")
+        h = x
+        for conv, block in zip(self.g_layers, blocks):
+            h = conv(block, h)
+        return h
 
 
 class GATPSPGNN(_ConvStack):
@@ -337,7 +342,9 @@ class SAGENet(_GNNNet):
         self._finish(node_embed_dim, out_ch)
 
     def forward_batch(self, blocks, x):
-        return self.sage.forward_batch(blocks, x)
+        """models.py:814-817: (n_out, n_embed) for the destination nodes of the last block."""
+        n_embed = self.sage.forward_batch(blocks, x)
+        return self.gnn_out(n_embed), n_embed
 
 
 class GATNet(_GNNNet):

@@ -181,9 +181,16 @@ class SAGEConv(nn.Module):
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
     def forward(self, g, feat):
+        """``g``: a batched Graph, or a sampled ``sampling.Block`` (``feat`` then has one row per SOURCE node and the
+        output one row per destination node: DGL's ``feat_dst = feat_src[:number_of_dst_nodes]``)."""
+        is_block = getattr(g, "is_block", False)
+        if is_block and feat.shape[0] != g.num_src_nodes:
+            raise SpgnnError(f"SAGEConv: block has {g.num_src_nodes} source nodes, features have {feat.shape[0]} rows")
         h = ops.concat_dropout(feat, None, self.feat_drop_p, self.training)
         m = ops.linear(h, self.fc_pool.weight, self.fc_pool.bias, "relu")
         neigh = ops.MaxPoolFn.apply(m, g)
+        if is_block:
+            h = h[:g.num_dst_nodes]
         # fc_self(h) + fc_neigh(neigh) as ONE two-source projection
         w = torch.cat([self.fc_self.weight, self.fc_neigh.weight], 1)
         b = self.bias

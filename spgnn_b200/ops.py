@@ -414,20 +414,23 @@ class SpmmFn(Function):
 
 
 class MaxPoolFn(Function):
-    """neigh[v] = max over in-neighbours (SAGEConv 'pool'), arg-slot saved for the backward scatter."""
+    """neigh[v] = max over in-neighbours (SAGEConv 'pool'), arg-slot saved for the backward scatter.  ``graph`` is a
+    batched Graph (square: rows of ``m`` = nodes) or a sampled ``sampling.Block`` (rows of ``m`` = source nodes,
+    output rows = destination nodes)."""
 
     @staticmethod
     def forward(ctx, m, graph):
         require_cuda(m)
         m = _rows(m)
-        N, F = m.shape
-        out = empty_padded(N, F, m.device)
-        arg = torch.empty(N, F, dtype=torch.int32, device=m.device)
+        n_src, F = m.shape
+        n_dst = int(getattr(graph, "num_dst_nodes", n_src))
+        out = empty_padded(n_dst, F, m.device)
+        arg = torch.empty(n_dst, F, dtype=torch.int32, device=m.device)
         lib().sage_maxpool_fwd(ptr(m), m.stride(0), ptr(graph.in_ptr), ptr(graph.in_src), ptr(out), out.stride(0),
-                               ptr(arg), N, F, stream(),
-                               _key=("bytes", 12.0 * N * F + 4.0 * (N + 1) + 4.0 * graph.num_edges))
+                               ptr(arg), n_dst, F, stream(),
+                               _key=("bytes", 4.0 * F * (n_src + 2 * n_dst) + 4.0 * (n_dst + 1) + 4.0 * graph.num_edges))
         ctx.save_for_backward(arg)
-        ctx.graph = graph
+        ctx.graph, ctx.n_src = graph, n_src
         return out
 
     @staticmethod
@@ -435,11 +438,11 @@ class MaxPoolFn(Function):
         (arg,) = ctx.saved_tensors
         gr = ctx.graph
         g = _rows(g)
-        N, F = g.shape
-        dm = empty_padded(N, F, g.device)
+        n_dst, F = g.shape
+        dm = empty_padded(ctx.n_src, F, g.device)
         lib().sage_maxpool_bwd(ptr(g), g.stride(0), ptr(arg), ptr(gr.out_ptr), ptr(gr.out_dst), ptr(gr.out_slot),
-                               ptr(dm), dm.stride(0), N, F, stream(),
-                               _key=("bytes", 12.0 * N * F + 8.0 * (N + 1) + 8.0 * gr.num_edges))
+                               ptr(dm), dm.stride(0), ctx.n_src, F, stream(),
+                               _key=("bytes", 4.0 * F * (ctx.n_src + 2 * n_dst) + 8.0 * (ctx.n_src + 1) + 8.0 * gr.num_edges))
         return dm, None
 
 

@@ -31,8 +31,8 @@ PRESETS = {
     "st_gin_3": dict(MODEL=dict(_COMMON, method="models.GINNet", num_gin_layers=3), SAMPLING_RATE=0.05,
                      JOB_RUNNER_CLS="job_runner.GCNTrain", TEST_RUNNER_CLS="job_runner.GCNTest"),
     "st_sage_3": dict(MODEL=dict(_COMMON, method="models.SAGENet", num_layers=3, feat_drop=0.1, node_ks=[2, 2, 2, 2],
-                                 node_sample_rate=0.3), SAMPLING_RATE=0.05,
-                      JOB_RUNNER_CLS="job_runner.GCNTrain", TEST_RUNNER_CLS="job_runner.GCNTest"),
+                                 node_sample_rate=0.3), SAMPLING_RATE=0.05, NODE_BATCH_SIZE=64, TRAIN_BATCH_SIZE=2,
+                      JOB_RUNNER_CLS="job_runner.GCNTrainSAGE", TEST_RUNNER_CLS="job_runner.GCNTest"),
     "st_pgat_spgnn_3": dict(MODEL=dict(_COMMON, **_GAT, method="models.GATPositionSPGNNNet", num_gat_layers=3,
                                        pos_hiddens=[256, 128, 64], num_pos_heads=1, pos_enc_dim=39),
                             SAMPLING_RATE=0.15, POS_ENC_DIM=39, JOB_RUNNER_CLS="job_runner.GCNTrainSPGNN",

@@ -104,7 +104,8 @@ def test_graph_errors(mods):
 # ------------------------------------------------------------------------------------------------ projection
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("M,K1,K2,N", [(300, 64, 0, 48), (1000, 1024, 39, 130), (257, 39, 0, 258), (513, 100, 7, 22),
-                                       (128, 64, 0, 16), (5000, 1024, 40, 1028), (4096, 192, 0, 4100)])
+                                       (128, 64, 0, 16), (5000, 1024, 40, 1028), (4096, 192, 0, 4100),
+                                       (64, 64, 0, 24), (10, 1024, 0, 256), (1, 128, 128, 64)])   # mini-batch sized
 def test_linear_fwd_bwd_against_fp64(mods, M, K1, K2, N, mode, monkeypatch):
     """mode 0: fp32 SIMT kernels; mode 1: tcgen05 split-bf16 tensor-core kernels with in-kernel conversion (falls
     back per call when an operand is not 16-byte aligned); mode 2 (the default): planes + TMA-fed tcgen05 GEMMs.
@@ -451,3 +452,51 @@ def test_pack_weight_matches_the_torch_formula(mods, H, F, K, res):
         if a is not None:
             assert a.grad.shape == a.shape
             assert rel_err(a.grad.cpu(), r.grad) < 1e-5
+
+
+def test_sage_forward_batch_on_sampled_blocks_vs_oracle(mods):
+    """SAGENet.forward_batch (models.py:685-689, 814-817) on MultiLayerNeighborSampler([2,2,2,2]) blocks: outputs,
+    loss and parameter gradients against the oracle run on the SAME blocks (the draw itself is torch's RNG)."""
+    from spgnn_b200 import sampling
+    kind, cfg = FULL_MODELS["st_sage_3"]
+    scans = _scan_dicts(mods, 500, 4, ragged=True)
+    g = _device_batch(mods, scans)
+    y = torch.from_numpy(np.concatenate([s["labels"] for s in scans]).astype(np.int64))
+    g.ndata["y"] = y.cuda()
+    torch.manual_seed(0)
+    onet = mods["om"].GNNNet(kind, cfg)
+    onet.init_like_reference()
+    onet.eval()
+    net = mods["sm"].SAGENet(**cfg).cuda()
+    net.load_state_dict(onet.state_dict(), strict=True)
+    net.eval()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    seeds = torch.randperm(g.num_nodes, device="cuda", generator=gen)[:64]
+    loader = sampling.NodeDataLoader(g, seeds, sampling.MultiLayerNeighborSampler(net.sage.node_ks), batch_size=64,
+                                     generator=gen)
+    (input_nodes, sd, blocks), = list(loader)
+    assert torch.equal(sd, seeds) and len(blocks) == 4 and blocks[-1].num_dst_nodes == 64
+    cw = torch.tensor([0.2] + [0.8] * 21)
+    out, emb = net.forward_batch(blocks, blocks[0].srcdata["fvs"])
+    loss = mods["ops"].masked_cross_entropy(out, blocks[-1].dstdata["y"], cw.cuda(), rate=1.0)
+    loss.backward()
+
+    oblocks = []
+    for b in blocks:
+        s_loc, d_loc = b.edges()
+        oblocks.append(mods["dgl_ops"].Block(s_loc.cpu(), d_loc.cpu(), b.num_src_nodes, b.num_dst_nodes))
+    ref_out, ref_emb = onet.forward_batch(oblocks, blocks[0].srcdata["fvs"].cpu())
+    loss_ref = torch.nn.functional.cross_entropy(ref_out, y[seeds.cpu()], weight=cw)
+    loss_ref.backward()
+    assert rel_err(out.detach().cpu(), ref_out.detach()) < TOL
+    assert rel_err(emb.detach().cpu(), ref_emb.detach()) < TOL
+    assert abs(loss.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
+    ograds = dict(onet.named_parameters())
+    gmax = max(float(q.grad.abs().max()) for q in ograds.values() if q.grad is not None)
+    for k, p in net.named_parameters():
+        r = ograds[k].grad
+        if r is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        abs_err = float((p.grad.cpu().double() - r.double()).abs().max())
+        assert abs_err <= 3e-2 * float(r.abs().max()) or abs_err <= 1e-6 * gmax, (k, abs_err, float(r.abs().max()))

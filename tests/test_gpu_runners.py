@@ -50,6 +50,8 @@ def test_other_presets_take_a_training_step(tmp_path, preset):
     from spgnn_b200.settings import get_callable_by_name
     s = _settings(tmp_path, preset, scans=3)
     tr = get_callable_by_name(s.JOB_RUNNER_CLS)(s)
+    from spgnn_b200 import job_runner
+    assert isinstance(tr, job_runner.GCNTrainSAGE) == (preset == "st_sage_3")     # neighbour-sampled mini-batches
     losses = tr.train_batch([tr.source(u) for u in tr.source.uids], steps=3)
     assert len(losses) == 3 and np.isfinite(losses).all()
     assert np.isfinite(tr.validate(tr.source.uids[:1]))
