@@ -159,11 +159,14 @@ int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, int64_t psc
 /* Elementwise half of a projection's backward in one pass: d = g * act'(y) (y = the forward OUTPUT; act NONE or
  * y NULL: d = g) written as planes [M, ldo] for planes_linear_bwd_input / _bwd_weight, plus (colsum_out != NULL) the
  * column sums of d = the bias gradient (row bands in ws, spgnn_act_bwd_planes_ws(N) bytes, reduced in fixed order).
- * g / y: fp32, 16-byte aligned rows padded to a multiple of 4 columns.  Replaces act_bwd + split_planes + colsum. */
+ * g / y: fp32, 16-byte aligned rows padded to a multiple of 4 columns.  Replaces act_bwd + split_planes + colsum.
+ * drop_p > 0: g is the gradient of a tensor that was dropped on its way into its consumer by
+ * spgnn_split_planes(p, seed) standing alone (chunk index row * ceil(N/4) + col/4): the same mask is applied to g
+ * first (Linear -> Dropout -> Linear chains, e.g. the GIN MLPs of models.py:358-383, without a dropout pass). */
 int64_t spgnn_act_bwd_planes_ws(int64_t N);
 int spgnn_act_bwd_planes(const float* g, int64_t ldg, const float* y, int64_t ldy, int act, float slope,
-                         uint16_t* out_hi, int64_t ldo, int64_t plane_stride, int64_t M, int64_t N,
-                         float* colsum_out, void* ws, void* stream);
+                         float drop_p, uint64_t drop_seed, uint16_t* out_hi, int64_t ldo, int64_t plane_stride,
+                         int64_t M, int64_t N, float* colsum_out, void* ws, void* stream);
 /* The launch plan planes_linear_bwd_weight would use (host only, no device work; for tests and profiling):
  * out[0..7] = {swap (1: the gradient dC is the M-side operand), np_tiles, nq_tiles, row splits, CTAs, rows per
  * split, 64-column blocks on the M side, on the N side}.  Returns the number of ints written (8). */

@@ -216,4 +216,19 @@ class GINConv(nn.Module):
     def forward(self, g, feat):
         _, _, in_inv, _ = g.norms()
         rst = ops.SpmmFn.apply(feat, self.eps, None, g, None, in_inv, 0, 0.0)
-        return self.apply_func(rst) if self.apply_func is not None else rst
+        mlp = self.apply_func
+        if mlp is None:
+            return rst
+        if ops.GEMM_MODE == 2 and _is_gin_mlp(mlp) and rst.is_cuda:
+            # the reference's MLP in one Function: no dropout pass in either direction (ops.MlpDropFn)
+            return ops.mlp_drop(rst, mlp[0].weight, mlp[0].bias, mlp[3].weight, mlp[3].bias, "leaky_relu",
+                                mlp[0]._slope, mlp[1].p if mlp[1].training else 0.0)
+        return mlp(rst)
+
+
+def _is_gin_mlp(mlp):
+    """Linear(leaky) → Dropout → [fused LeakyReLU] → Linear(leaky) → [fused LeakyReLU], as models.GIN builds it."""
+    return (isinstance(mlp, nn.Sequential) and len(mlp) == 5 and isinstance(mlp[0], Linear) and
+            isinstance(mlp[1], Dropout) and isinstance(mlp[2], LeakyReLU) and mlp[2].fused and
+            isinstance(mlp[3], Linear) and isinstance(mlp[4], LeakyReLU) and mlp[4].fused and
+            mlp[0]._act == "leaky_relu" and mlp[3]._act == "leaky_relu" and mlp[0]._slope == mlp[3]._slope)

@@ -190,7 +190,7 @@ class PlanesLinearFn(Function):
             db = torch.empty(N, dtype=torch.float32, device=g.device) if want_db else None
             ws = _ws(L.act_bwd_planes_ws(N), g.device) if want_db else None
             L.act_bwd_planes(ptr(g), g.stride(0), ptr(y) if act else None, y.stride(0) if act else 0, act, slope,
-                             gp.ptr(), gp.ld, gp.ps, M, N, ptr(db), ptr(ws), stream(),
+                             0.0, 0, gp.ptr(), gp.ld, gp.ps, M, N, ptr(db), ptr(ws), stream(),
                              _key=("bytes", (12.0 if act else 8.0) * M * N))
             want_db = False
         else:
@@ -210,6 +210,67 @@ class PlanesLinearFn(Function):
         if want_db:
             db = colsum(g)
         return dx1, dx2, dW, db, None, None
+
+
+class MlpDropFn(Function):
+    """y = act(W3 · dropout(act(W0·x + b0), p) + b3) — the MLP of the reference's GINConv layers (Linear → Dropout(0.1)
+    → LeakyReLU → Linear → LeakyReLU, models.py:358-383, with the activation moved in front of the dropout: the two
+    commute) — without a dropout pass in either direction: the mask is applied where the hidden activation is converted
+    to planes for the second projection (``spgnn_split_planes(p, seed)``) and, in the backward, where the gradient of
+    the dropped tensor is read by the fused ``spgnn_act_bwd_planes`` pass (same (seed, chunk) hash)."""
+
+    @staticmethod
+    def forward(ctx, x, W0, b0, W3, b3, act, slope, p, seed):
+        from . import stack
+        require_cuda(x, W0, b0, W3, b3)
+        W0, W3 = _rows(W0), _rows(W3)
+        if W0.shape[1] != x.shape[1] or W3.shape[1] != W0.shape[0]:
+            raise SpgnnError(f"mlp: shapes {tuple(x.shape)} -> {tuple(W0.shape)} -> {tuple(W3.shape)} do not chain")
+        P0 = _planes_of(x)
+        y1 = stack.planes_linear(P0, W0, b0.contiguous() if b0 is not None else None, act, float(slope))
+        P1 = stack.split_planes(y1, float(p), seed)
+        y2 = stack.planes_linear(P1, W3, b3.contiguous() if b3 is not None else None, act, float(slope))
+        ctx.planes = (P0, P1)
+        ctx.save_for_backward(W0, W3, y1, y2)
+        ctx.cfg = (act, float(slope), float(p), seed, b0 is not None, b3 is not None)
+        return y2
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import stack
+        W0, W3, y1, y2 = ctx.saved_tensors
+        act, slope, p, seed, has_b0, has_b3 = ctx.cfg
+        P0, P1 = ctx.planes
+        ctx.planes = None
+        L = lib()
+        dev = g.device
+        M = y1.shape[0]
+        need = ctx.needs_input_grad
+
+        def glue(gr, y, drop_p, drop_seed, want_db):
+            """planes of mask(gr) * act'(y) and (optionally) their column sums"""
+            gr = stack._grad_rows(gr)
+            n = y.shape[1]
+            gp = stack.Planes(M, n, dev)
+            db = torch.empty(n, dtype=torch.float32, device=dev) if want_db else None
+            ws = _ws(L.act_bwd_planes_ws(n), dev) if want_db else None
+            L.act_bwd_planes(ptr(gr), gr.stride(0), ptr(y) if act else None, y.stride(0) if act else 0, act, slope,
+                             drop_p, drop_seed, gp.ptr(), gp.ld, gp.ps, M, n, ptr(db), ptr(ws), stream(),
+                             _key=("bytes", (12.0 if act else 8.0) * M * n))
+            return gp, db
+
+        gp2, db3 = glue(g, y2, 0.0, 0, has_b3 and need[4])
+        dW3 = stack.planes_linear_bwd_weight(gp2, P1) if need[3] else None
+        dy1 = stack.planes_linear_bwd_input(gp2, W3, W3.shape[1])          # gradient of the DROPPED hidden tensor
+        del gp2
+        gp1, db0 = glue(dy1, y1, p, seed, has_b0 and need[2])
+        dW0 = stack.planes_linear_bwd_weight(gp1, P0) if need[1] else None
+        dx = stack.planes_linear_bwd_input(gp1, W0, W0.shape[1]) if need[0] else None
+        return dx, dW0, db0, dW3, db3, None, None, None, None
+
+
+def mlp_drop(x, W0, b0, W3, b3, act="leaky_relu", slope=0.01, p=0.0):
+    return MlpDropFn.apply(x, W0, b0, W3, b3, act_code(act), slope, float(p), next_seed() if p > 0.0 else 0)
 
 
 def linear(x1, W, bias=None, act=None, slope=0.0, x2=None):

@@ -500,3 +500,36 @@ def test_sage_forward_batch_on_sampled_blocks_vs_oracle(mods):
             continue
         abs_err = float((p.grad.cpu().double() - r.double()).abs().max())
         assert abs_err <= 3e-2 * float(r.abs().max()) or abs_err <= 1e-6 * gmax, (k, abs_err, float(r.abs().max()))
+
+
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_gin_mlp_function_with_fused_dropout(mods, p):
+    """ops.MlpDropFn (GIN's Linear → Dropout → LeakyReLU → Linear → LeakyReLU) against fp64 autograd with the SAME
+    dropout mask (regenerated from the seed through spgnn_split_planes): outputs and all five gradients."""
+    from spgnn_b200 import stack
+    ops = mods["ops"]
+    M, a, b = 700, 96, 64
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(M, a, generator=gen)
+    W0, b0 = torch.randn(b, a, generator=gen) / a ** 0.5, torch.randn(b, generator=gen) * 0.1
+    W3, b3 = torch.randn(b, b, generator=gen) / b ** 0.5, torch.randn(b, generator=gen) * 0.1
+    go = torch.randn(M, b, generator=gen)
+    seed = 0x1234ABCD
+    leaves = [t.cuda().requires_grad_() for t in (x, W0, b0, W3, b3)]
+    y = ops.MlpDropFn.apply(*leaves, ops.act_code("leaky_relu"), 0.01, p, seed)
+    y.backward(go.cuda())
+    # the mask, from the hidden activation and its dropped planes
+    with torch.no_grad():
+        y1 = ops.linear(leaves[0].detach(), leaves[1].detach(), leaves[2].detach(), "leaky_relu", 0.01)
+        dropped = stack.split_planes(y1, p, seed).float()
+        scale = torch.where(y1 != 0, dropped / y1, torch.ones_like(y1)).cpu().double()
+    if p > 0:
+        kept = (scale > 0).double().mean().item()
+        assert abs(kept - (1 - p)) < 0.02 and torch.allclose(scale[scale > 0], torch.tensor(1 / (1 - p), dtype=torch.float64), rtol=1e-3)
+    ref = [t.double().requires_grad_() for t in (x, W0, b0, W3, b3)]
+    lk = torch.nn.functional.leaky_relu
+    yr = lk((lk(ref[0] @ ref[1].t() + ref[2], 0.01) * scale) @ ref[3].t() + ref[4], 0.01)
+    yr.backward(go.double())
+    assert rel_err(y.detach().cpu(), yr.detach()) < 4e-5
+    for t, r in zip(leaves, ref):
+        assert rel_err(t.grad.cpu(), r.grad) < 1e-4, t.shape
