@@ -527,8 +527,11 @@ def test_gin_mlp_function_with_fused_dropout(mods, p):
         kept = (scale > 0).double().mean().item()
         assert abs(kept - (1 - p)) < 0.02 and torch.allclose(scale[scale > 0], torch.tensor(1 / (1 - p), dtype=torch.float64), rtol=1e-3)
     ref = [t.double().requires_grad_() for t in (x, W0, b0, W3, b3)]
-    lk = torch.nn.functional.leaky_relu
-    yr = lk((lk(ref[0] @ ref[1].t() + ref[2], 0.01) * scale) @ ref[3].t() + ref[4], 0.01)
+    # LeakyReLU branches taken from the device outputs: an element within fp32 rounding of the kink would otherwise
+    # flip its derivative (1 vs 0.01) between the fp32 and the fp64 evaluation and move a whole gradient row
+    s1 = torch.where(y1 > 0, 1.0, 0.01).cpu().double()
+    s2 = torch.where(y.detach() > 0, 1.0, 0.01).cpu().double()
+    yr = (((ref[0] @ ref[1].t() + ref[2]) * s1 * scale) @ ref[3].t() + ref[4]) * s2
     yr.backward(go.double())
     assert rel_err(y.detach().cpu(), yr.detach()) < 4e-5
     for t, r in zip(leaves, ref):
