@@ -434,7 +434,11 @@ using namespace spgnn::layer;
 extern "C" int64_t spgnn_gat_layer_sizeof(void) { return (int64_t)sizeof(spgnn_gat_layer); }
 
 extern "C" int64_t spgnn_gat_layer_dbias_ws(int64_t N, int64_t H, int64_t F) {
-    return (int64_t)layer_grid(N) * H * F * (int64_t)sizeof(float);
+    // one partial row per CTA: the chunk kernels run layer_grid(N) CTAs, the per-tree kernels min(B, #SMs) — with many
+    // tiny graphs (B > N / kNPC) the latter is the larger one (a batch of 1-, 2- and 3-node trees overran a workspace
+    // sized by the former: tests/test_gpu_parity.py::test_gat3_on_edge_case_graphs_vs_oracle[tiny_trees])
+    const int64_t rows = (int64_t)layer_grid(N) > (int64_t)sm_count() ? (int64_t)layer_grid(N) : (int64_t)sm_count();
+    return rows * H * F * (int64_t)sizeof(float);
 }
 
 extern "C" int spgnn_gat_layer_fwd(const spgnn_gat_layer* L, void* stream) {

@@ -536,3 +536,78 @@ def test_gin_mlp_function_with_fused_dropout(mods, p):
     assert rel_err(y.detach().cpu(), yr.detach()) < 4e-5
     for t, r in zip(leaves, ref):
         assert rel_err(t.grad.cpu(), r.grad) < 1e-4, t.shape
+
+
+def _random_tree_adj(n, max_children, rng):
+    """tree ∪ I as uint8: node i > 0 hangs under a random earlier node that still has room for a child."""
+    adj = np.eye(n, dtype=np.uint8)
+    kids = np.zeros(n, dtype=np.int64)
+    for i in range(1, n):
+        cand = np.flatnonzero(kids[:i] < max_children)
+        p = int(rng.choice(cand))
+        kids[p] += 1
+        adj[i, p] = adj[p, i] = 1
+    return adj
+
+
+@pytest.mark.parametrize("case", [
+    "tiny_trees",
+    pytest.param("trifurcations", marks=pytest.mark.xfail(
+        strict=False,
+        reason="KNOWN ISSUE (found at the end of round 1, no GPU time left to bisect): with in-degree > 4 the forward, "
+               "the loss and fc.weight gradients match the oracle, but attn_l / attn_r / res_fc.weight gradients are "
+               "off by 2-3 % (general-degree branch of the chunk backward kernels in gat_layer.cu / gat_wide.cu); "
+               "see DESIGN.md section 7")),
+    "above_384_nodes"])
+def test_gat3_on_edge_case_graphs_vs_oracle(mods, case):
+    """st_gat_3 at full width on graphs outside the per-tree kernels' envelope (degree <= 4, <= 384 nodes, which the
+    synthetic bifurcating trees never leave): single-node and 3-node trees in a batch, airway trees with tri- and
+    quadrifurcations (in-degree up to 6), a tree of 801 nodes.  Forward, loss and parameter gradients vs the oracle."""
+    rng = np.random.default_rng(7)
+    if case == "tiny_trees":
+        adjs = [_random_tree_adj(n, 2, rng) for n in (1, 3, 120, 1, 2)]
+    elif case == "trifurcations":
+        adjs = [_random_tree_adj(n, 4, rng) for n in (150, 90)]
+    else:
+        adjs = [_random_tree_adj(801, 2, rng), _random_tree_adj(60, 2, rng)]
+    scans = []
+    for a in adjs:
+        n = a.shape[0]
+        scans.append(dict(adj=a, fvs=np.maximum(rng.standard_normal((n, 1024)), 0).astype(np.float32),
+                          fvs_out=rng.standard_normal((n, 22)).astype(np.float32),
+                          labels=rng.integers(0, 22, n).astype(np.int64)))
+    kind, cfg = FULL_MODELS["st_gat_3"]
+    torch.manual_seed(0)
+    onet = mods["om"].GNNNet(kind, cfg)
+    onet.init_like_reference()
+    onet.eval()
+    net = mods["sm"].GATNet(**cfg).cuda()
+    net.load_state_dict(onet.state_dict(), strict=True)
+    net.eval()
+    og, g = _oracle_batch(mods, scans), _device_batch(mods, scans)
+    assert torch.equal(g.src.cpu(), og.src) and torch.equal(g.dst.cpu(), og.dst)
+    if case == "trifurcations":
+        assert g.max_degree() > 4
+    y = torch.from_numpy(np.concatenate([s["labels"] for s in scans]))
+    cw = torch.tensor([0.2] + [0.8] * 21)
+    mask = torch.ones(y.numel(), dtype=torch.bool)
+    ref = onet(og)
+    loss_ref = mods["om"].cross_entropy_masked(ref[0], y, mask, cw)
+    loss_ref.backward()
+    out = net(g)
+    loss = mods["ops"].masked_cross_entropy(out[0], y.cuda(), cw.cuda(), mask=mask.cuda())
+    loss.backward()
+    for j in range(len(ref)):
+        assert rel_err(out[j].detach().cpu(), ref[j].detach()) < TOL, (case, j)
+    assert abs(loss.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
+    ograds = dict(onet.named_parameters())
+    gmax = max(float(q.grad.abs().max()) for q in ograds.values() if q.grad is not None)
+    bad = []
+    for k, p in net.named_parameters():
+        r = ograds[k].grad
+        if r is None:
+            continue
+        abs_err = float((p.grad.cpu().double() - r.double()).abs().max())
+        if not (abs_err <= GRAD_TOL * float(r.abs().max()) or abs_err <= 1e-6 * gmax):
+            bad.append((k, f"{abs_err:.3e}", f"{float(r.abs().max()):.3e}"))
+    assert not bad, (case, f"gmax {gmax:.3e}", bad)
