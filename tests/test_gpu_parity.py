@@ -554,9 +554,9 @@ def _random_tree_adj(n, max_children, rng):
     "tiny_trees",
     pytest.param("trifurcations", marks=pytest.mark.xfail(
         strict=False,
-        reason="KNOWN ISSUE (found at the end of round 1, no GPU time left to bisect): with in-degree > 4 the forward, "
-               "the loss and fc.weight gradients match the oracle, but attn_l / attn_r / res_fc.weight gradients are "
-               "off by 2-3 % (general-degree branch of the chunk backward kernels in gat_layer.cu / gat_wide.cu); "
+        reason="KNOWN ISSUE (found at the end of round 1, no GPU time left to bisect): with in-degree > 4 the forward and "
+               "the loss match the oracle, but parameter gradients (attn_l, attn_r, res_fc.weight, ...) are off by "
+               "2-3 % (general-degree branch of the chunk backward kernels in gat_layer.cu / gat_wide.cu); "
                "see DESIGN.md section 7")),
     "above_384_nodes"])
 def test_gat3_on_edge_case_graphs_vs_oracle(mods, case):
