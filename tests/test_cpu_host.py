@@ -182,3 +182,24 @@ def test_flat_sgd_gathers_gradients_into_one_bucket():
     assert torch.equal(opt.flat_g, torch.cat([r.reshape(-1) for r in ref]))
     opt.zero_grad()
     assert all(p.grad is None for p in net.parameters())
+
+
+def test_bench_workloads_and_launch_list_summary():
+    """bench.py's preset table covers every BASELINE.json config, the headline keeps its metric name, and the
+    committed ncu launch list summarises to the step the docs quote (one training step = 109 launches)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, kind in (("st_pgat_spgnn_3", "spgnn"), ("st_gat_3", "gat"), ("st_gat_6", "gat"), ("st_gat_6_nr", "gat"),
+                       ("st_gcn_3", "gcn"), ("st_gin_3", "gin"), ("st_sage_3", "sage")):
+        model, k, method, rate = bench.workload(name)
+        assert k == kind and "method" not in model and 0.0 < rate < 1.0 and method.startswith("models.")
+    assert bench.metric_name(bench.HEADLINE) == "spgnn3_train_graphs_per_s"
+    assert bench.metric_name("st_gcn_3") == "st_gcn_3_train_graphs_per_s"
+    csv_path = os.path.join(ROOT, "profiles", "r01_launches_final.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "launch_summary.py"), csv_path],
+                         capture_output=True, text=True, check=True).stdout
+    first = out.splitlines()[0]
+    assert first.startswith("one training step: launches 109"), first
+    assert "tn_planes_kernel" in out and "gat_tree_bwd_kernel" in out
