@@ -412,6 +412,12 @@ int spgnn_masked_ce_bwd(const float* logits, int64_t ld, int64_t n_class, const 
 /* SGD with momentum over a flat bucket (torch.optim.SGD semantics: buf = mu*buf + g; p -= lr*buf). */
 int spgnn_sgd_momentum(float* p, const float* g, float* buf, int64_t n, float lr, float mu, float grad_scale,
                        int first_step, void* stream);
+/* The full update of torch.optim.SGD (the reference's optimiser, job_runner.py:239-249 with
+ * exp_settings OPTIMIZER = {momentum, lr[, weight_decay, dampening, nesterov]}) over a contiguous range of the bucket:
+ *   g = grad_scale*g + weight_decay*p;  buf = first_step ? g : mu*buf + (1-dampening)*g  (mu != 0);
+ *   g = nesterov ? g + mu*buf : buf;  p -= lr*g.   buf may be null when mu == 0. */
+int spgnn_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float mu, float dampening,
+                   float weight_decay, int nesterov, float grad_scale, int first_step, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Synthetic airway trees on device (bench input; integer part bit-identical to spgnn_b200/synth.py).

@@ -21,6 +21,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import kinks
+
 VERSION_SWITCHES = {
     "gat_bias": True,
     "gat_res_identity_rule": "in!=F",
@@ -216,12 +218,12 @@ class GATConv(nn.Module):
         if not self.allow_zero_in_degree and bool((g.in_degrees() == 0).any()):
             raise RuntimeError("There are 0-in-degree nodes in the graph (DGLError in the reference stack)")
         n, H, Fo = g.num_nodes, self._heads, self._out
-        h = self.feat_drop(feat)                                   # K0
-        z = self.fc(h).view(n, H, Fo)                              # K1
+        h = kinks.dropout(self.feat_drop, feat)                    # K0 (kinks.*: the plain torch op unless a test
+        z = self.fc(h).view(n, H, Fo)                              # K1  replays the device's decisions, oracle/kinks.py)
         el = (z * self.attn_l).sum(-1, keepdim=True)               # K2
         er = (z * self.attn_r).sum(-1, keepdim=True)
-        e = F.leaky_relu(el[g.src] + er[g.dst], self.negative_slope)   # K3, K4
-        a = self.attn_drop(edge_softmax(g, e))                     # K5, K6
+        e = kinks.leaky_relu(el[g.src] + er[g.dst], self.negative_slope)   # K3, K4
+        a = kinks.dropout(self.attn_drop, edge_softmax(g, e))      # K5, K6
         rst = _seg_sum(z[g.src] * a, g.dst, n)                     # K7
         if self.res_fc is not None:                                # K8
             rst = rst + self.res_fc(h).view(n, -1, Fo)
@@ -308,15 +310,14 @@ class SAGEConv(nn.Module):
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
     def forward(self, g, feat):
-        h = self.feat_drop(feat)
-        m = F.relu(self.fc_pool(h))
+        h = kinks.dropout(self.feat_drop, feat)
+        m = kinks.relu(self.fc_pool(h))
         if isinstance(g, Block):                   # DGL: feat_dst = feat_src[:number_of_dst_nodes()]
             n = g.num_dst
             h = h[:n]
         else:
             n = g.num_nodes
-        neigh = _seg_max(m[g.src], g.dst, n)
-        neigh = torch.where(torch.isinf(neigh), torch.zeros_like(neigh), neigh)   # DGL zero-fills empty rows
+        neigh = kinks.seg_max_nodes(m, g.src, g.dst, n)            # max over in-neighbours; DGL zero-fills empty rows
         rst = self.fc_self(h) + self.fc_neigh(neigh)
         if self.bias is not None:
             rst = rst + self.bias

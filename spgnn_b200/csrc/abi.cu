@@ -25,6 +25,13 @@ int sm_count() {
     }
     return cached;
 }
+static unsigned long long device_bit() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return 0ull;      // unknown device: never cached
+    return 1ull << dev;
+}
+bool DeviceOnce::pending() const { return (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) & device_bit()) == 0ull; }
+void DeviceOnce::done() { __atomic_fetch_or(&mask, device_bit(), __ATOMIC_RELEASE); }
 }  // namespace spgnn
 
 extern "C" const char* spgnn_last_error(void) { return spgnn::g_err; }

@@ -38,6 +38,14 @@ void count_launch();
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int sm_count();
+// One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device property: a process-wide flag would leave a second
+// GPU, or the device after a cudaDeviceReset, without the opt-in to > 48 KB of dynamic shared memory).  pending()
+// is true until done() was called for the current device; setting an attribute twice from two threads is harmless.
+struct DeviceOnce {
+    unsigned long long mask = 0;
+    bool pending() const;
+    void done();
+};
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -494,10 +494,10 @@ extern "C" int spgnn_gat_layer_bwd(const spgnn_gat_layer* L, void* stream) {
     if (rc || handled) return rc;
     const unsigned grid = layer_grid(a.N);
     const size_t smem_dst = stage_bytes(a.H, HF, true);
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(gat_layer_bwd_dst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
+        attr.done();
     }
     gat_layer_bwd_dst_kernel<<<grid, kThreads, smem_dst, st>>>(a);
     SPGNN_LAUNCH_OK();

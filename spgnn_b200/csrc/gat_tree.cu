@@ -574,10 +574,10 @@ int launch_fwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* h
     t.nstages = fwd_smem_bytes(t.nmax, a.H, 2) <= kSmemLimit ? 2 : 1;
     const size_t smem = fwd_smem_bytes(t.nmax, a.H, t.nstages);
     if (smem > kSmemLimit) return SPGNN_OK;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(gat_tree_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        attr = true;
+        attr.done();
     }
     const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
     gat_tree_fwd_kernel<<<grid, kThreads, smem, st>>>(zmap, t);
@@ -597,11 +597,11 @@ int launch_bwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* h
     t.nstages = bwd_smem_bytes(t.nmax, a.H, HF, 2) <= kSmemLimit ? 2 : 1;
     const size_t smem = bwd_smem_bytes(t.nmax, a.H, HF, t.nstages);
     if (smem > kSmemLimit) return SPGNN_OK;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(gat_tree_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         SPGNN_CUDA_OK(cudaFuncSetAttribute(gat_tree_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        attr = true;
+        attr.done();
     }
     const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
     if (a.n_g == 1) gat_tree_bwd_kernel<1><<<grid, kThreads, smem, st>>>(zmap, t);

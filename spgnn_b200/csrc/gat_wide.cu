@@ -82,6 +82,8 @@ __device__ __forceinline__ Stage carve(uint8_t* smem, int H) {
 static size_t stage_bytes(int H, int k4) {
     return (size_t)kNPC * 6 * 4 + (size_t)kNPC * H * 4 * 4 * 4 + (size_t)2 * H * k4 * 4 + 16;
 }
+// the forward only stages deg | beg | nb | w (at / lk / dd / we belong to the backward): independent of k_in
+static size_t stage_bytes_fwd(int H) { return (size_t)kNPC * 6 * 4 + (size_t)kNPC * H * 4 * 4 + 16; }
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int H>
@@ -457,7 +459,7 @@ extern "C" int spgnn_gat_aggx_fwd(const spgnn_gat_wide* L, void* stream) {
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
     const unsigned grid = wide_grid(a.N);
-    const size_t smem = stage_bytes(a.H, a.k4);
+    const size_t smem = stage_bytes_fwd(a.H);
     WIDE_DISPATCH(aggx_fwd_kernel, a);
     return SPGNN_OK;
 }

@@ -783,7 +783,7 @@ static void pick_bn(int N, int* BN, int* nt) {
     *BN = round_up((n16 + *nt - 1) / *nt, 16);
 }
 
-static bool g_attr_set_nt = false, g_attr_set_tn = false;
+static DeviceOnce g_attr_set_nt, g_attr_set_tn;
 
 }  // namespace tc
 
@@ -795,9 +795,9 @@ int64_t tc_linear_ws_bytes(int64_t N, int64_t K1, int64_t K2) {
 }
 
 static int launch_nt(const NtArgs& a, cudaStream_t st) {
-    if (!g_attr_set_nt) {
+    if (g_attr_set_nt.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(tc_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        g_attr_set_nt = true;
+        g_attr_set_nt.done();
     }
     const int64_t tiles = a.nt_m * a.nt_n;
     const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
@@ -875,9 +875,9 @@ void reduce_splits(const float* ws, int64_t splits, int64_t N, int64_t K, float*
 
 int tc_linear_bwd_weight(const float* dC, int64_t lddc, const float* A, int64_t lda, float* dW, int64_t lddw,
                          int64_t k_off, int64_t M, int64_t N, int64_t K, void* ws, cudaStream_t st) {
-    if (!g_attr_set_tn) {
+    if (g_attr_set_tn.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTnSmemBytes));
-        g_attr_set_tn = true;
+        g_attr_set_tn.done();
     }
     int64_t splits, rows;
     tn_plan(M, N, K, &splits, &rows);
@@ -894,7 +894,7 @@ int tc_linear_bwd_weight(const float* dC, int64_t lddc, const float* A, int64_t 
 }
 
 
-static bool g_attr_set_tn2 = false;
+static DeviceOnce g_attr_set_tn2;
 
 static void tn2_plan(int64_t M, int64_t N, int64_t K1, int64_t K2, int* BN, int* nt_n, int* nk1, int* nk2,
                      int64_t* splits, int64_t* rows) {
@@ -922,9 +922,9 @@ int64_t tc_linear_bwd_weight2_ws_bytes(int64_t M, int64_t N, int64_t K1, int64_t
 int tc_linear_bwd_weight2(const float* dC, int64_t lddc, const float* X1, int64_t ldx1, int64_t K1, const float* X2,
                           int64_t ldx2, int64_t K2, float* dW, int64_t lddw, int64_t M, int64_t N, void* ws,
                           cudaStream_t st) {
-    if (!g_attr_set_tn2) {
+    if (g_attr_set_tn2.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(tc::tc_tn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::T2_SMEM));
-        g_attr_set_tn2 = true;
+        g_attr_set_tn2.done();
     }
     tc::Tn2Args a{};
     int64_t splits, rows;

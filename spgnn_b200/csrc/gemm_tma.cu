@@ -863,9 +863,9 @@ static unsigned split_grid(int64_t total) {
 static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t K1, const __nv_bfloat16* A2,
                      int64_t lda2, int64_t ps2, int64_t K2, const __nv_bfloat16* Bhi, int64_t ldb, const float* bias,
                      int act, float slope, float* C, int64_t ldc, int64_t M, int64_t N, cudaStream_t st) {
-    static bool attr = false;
+    static DeviceOnce attr;
     static int max_clusters = 0;             // co-resident 2-CTA clusters (0: cluster launches unavailable)
-    if (!attr) {
+    if (attr.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_planes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_planes_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         // opt-in: measured neutral on B200 (profiles/r01_gemm_check_cluster_vs_plain.txt) - the projections are
@@ -882,7 +882,7 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
             if (cudaOccupancyMaxActiveClusters(&n, nt_planes_kernel<2>, &cfg) == cudaSuccess) max_clusters = n;
             else (void)cudaGetLastError();
         }
-        attr = true;
+        attr.done();
     }
     NtMaps maps;
     NtArgs a{};
@@ -1024,10 +1024,10 @@ extern "C" int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa,
         a.dpre = reinterpret_cast<__nv_bfloat16*>(dpre); a.ldd = ldd; a.psd = psd;
     }
     cudaStream_t st = as_stream(stream);
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        attr = true;
+        attr.done();
     }
     const int nparts = has_res ? 2 : 1;
     const int64_t HF = (int64_t)H * F, ldb = nparts * kp;
@@ -1200,10 +1200,10 @@ extern "C" int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, 
     SPGNN_REQUIRE(lddw >= K1 + K2, "planes_linear_bwd_weight: leading dimension too small");
     SPGNN_REQUIRE(ws_bytes >= spgnn_planes_linear_bwd_weight_ws(M, N, K1, K2), "planes_linear_bwd_weight: workspace too small");
     SPGNN_REQUIRE(M < (1ll << 31), "planes_linear_bwd_weight: too many rows");
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(tn_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
-        attr = true;
+        attr.done();
     }
     cudaStream_t st = as_stream(stream);
     const TnPlan t = tn_plan(M, N, K1, K2);

@@ -78,6 +78,23 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
     }
 }
 
+// torch.optim.SGD._single_tensor_sgd (torch/optim/sgd.py): g += wd*p; buf = first ? g : mu*buf + (1-damp)*g;
+// g = nesterov ? g + mu*buf : buf (only with momentum); p -= lr*g
+__global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n,
+                                float lr, float mu, float damp, float wd, int nesterov, float gs, int first) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float pi = p[i];
+        float gi = g[i] * gs;
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        if (mu != 0.f) {
+            const float b = first ? gi : fmaf(mu, buf[i], (1.f - damp) * gi);
+            buf[i] = b;
+            gi = nesterov ? fmaf(mu, b, gi) : b;
+        }
+        p[i] = pi - lr * gi;
+    }
+}
+
 static inline unsigned egrid(int64_t n) {
     int64_t want = ceil_div(n, kT), cap = (int64_t)sm_count() * 8;
     if (want < 1) want = 1;
@@ -107,6 +124,16 @@ extern "C" int spgnn_masked_ce_bwd(const float* logits, int64_t ld, int64_t n_cl
                   "masked_ce_bwd: bad argument");
     masked_ce_bwd_kernel<<<egrid(N), kT, 0, as_stream(stream)>>>(logits, ld, (int)n_class, y, mask, rate, seed, class_w,
                                                                  sums, scale, N, dlogits, ldd);
+    SPGNN_LAUNCH_OK();
+    return SPGNN_OK;
+}
+
+extern "C" int spgnn_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float mu, float dampening,
+                              float weight_decay, int nesterov, float grad_scale, int first_step, void* stream) {
+    SPGNN_REQUIRE(p && g && n > 0 && (buf || mu == 0.f), "sgd_step: bad argument");
+    SPGNN_REQUIRE(!nesterov || (mu > 0.f && dampening == 0.f), "sgd_step: nesterov needs momentum > 0 and dampening == 0");
+    sgd_step_kernel<<<egrid(n), kT, 0, as_stream(stream)>>>(p, g, buf, n, lr, mu, dampening, weight_decay, nesterov,
+                                                           grad_scale, first_step);
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }

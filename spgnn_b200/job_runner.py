@@ -93,6 +93,10 @@ class _Runner:
         if isinstance(self.settings, str):
             self.settings = Settings(self.settings)
         s = self.settings
+        if self._always_reload:                       # BaselineTest.__init__ (job_runner.py:566-575): testing reloads
+            s.RELOAD_CHECKPOINT = True
+            if cpk_path is not None:
+                s.RELOAD_CHECKPOINT_PATH = cpk_path
         self.output_path = output_path
         self.logger = logging.getLogger(type(self).__name__)
         if not torch.cuda.is_available():
@@ -108,34 +112,75 @@ class _Runner:
         cw = [s.CLASS_WEIGHTS[k] for k in sorted(s.CLASS_WEIGHTS.keys())][1:]          # job_runner.py:1867
         self.class_w = torch.tensor(cw, dtype=torch.float32, device=self.device)
         self.pos_enc_dim = getattr(s, "POS_ENC_DIM", 39) if self.uses_pos_enc else 0
-        if s.RELOAD_CHECKPOINT or s.RELOAD_CHECKPOINT_PATH:
+        self.optimizer = None                         # training runners build it before reloading
+        self.base_lr = None
+        self.metric = {}                              # the reference's model_metrics_save_dict
+        if type(self)._reload_in_base:
             self.reload_model_from_cache()
 
-    # ---- checkpoints: same container keys as job_runner.py:345-350
+    _reload_in_base = True
+    _always_reload = False
+
+    # ---- checkpoints: the container of job_runner.py:336-350 (update_model_state / save_model)
     def save_model(self, **kwargs):
         os.makedirs(self.exp_path, exist_ok=True)
+        if "metric" in kwargs and not isinstance(kwargs["metric"], dict):
+            self.metric = {"metric": kwargs.pop("metric")}
         state = {"iteration": self.current_iteration, "epoch_n": self.epoch_n,
                  "model_dict": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
-                 "metric": kwargs.get("metric")}
+                 "metric": dict(self.metric)}
+        if self.optimizer is not None:
+            state["optimizer_dict"] = self.optimizer.state_dict()
+            state["scheduler_dict"] = {"gamma": getattr(self, "gamma", 1.0), "base_lrs": [self.base_lr],
+                                       "last_epoch": self.epoch_n, "_last_lr": [self.optimizer.lr]}
+        state.update(kwargs)
         path = os.path.join(self.exp_path, f"{self.current_iteration}.pth")
         torch.save(state, path)
+        self.logger.info("saved model into %s.", path)
         return path
 
     def reload_model_from_cache(self):
-        path = self.settings.RELOAD_CHECKPOINT_PATH
+        """job_runner.py:298-331 + load_pretrained_model (:87-123): only when RELOAD_CHECKPOINT is set; an explicit
+        RELOAD_CHECKPOINT_PATH or the newest ``*.pth`` of the experiment; a missing checkpoint is logged and training
+        starts from scratch; RELOAD_DICT_LIST names, position by position, which of (model, metric, optimizer,
+        scheduler) are restored; model tensors whose shape differs are skipped; iteration resumes at saved + 1."""
+        s = self.settings
+        if not s.RELOAD_CHECKPOINT:
+            return None
+        path = s.RELOAD_CHECKPOINT_PATH
         if path is None:
-            found = sorted(glob.glob(os.path.join(self.exp_path, "*.pth")), key=os.path.getmtime)
+            found = glob.glob(os.path.join(self.exp_path, "*.pth"))
             if not found:
-                raise SpgnnError(f"no checkpoint under {self.exp_path}")
-            path = found[-1]
+                self.logger.error("%s has no checkpoint files with pth extensions.", self.exp_path)
+                return None
+            path = max(found, key=os.path.getctime)
+        self.logger.info("reloading model from %s.", path)
         state = torch.load(path, map_location="cpu", weights_only=False)
-        own = self.model.state_dict()
-        # job_runner.py:100-104: keys present in both with equal shapes are loaded, the rest skipped
-        ok = {k: v for k, v in state["model_dict"].items() if k in own and own[k].shape == v.shape}
-        self.model.load_state_dict(ok, strict=False)
+        ignored = set(getattr(s, "RELOAD_CHECKPOINT_IGNORE", []) or [])
+        slots = ("model", "metric", "optimizer", "scheduler")
+        for slot, key in zip(slots, s.RELOAD_DICT_LIST):
+            if key not in state:
+                continue
+            if slot == "model":
+                own = self.model.state_dict()
+                ok = {k: v for k, v in state[key].items()
+                      if k in own and k not in ignored and own[k].shape == v.shape}
+                self.model.load_state_dict(ok, strict=False)
+                self.logger.info("loaded %d/%d tensors from %s", len(ok), len(own), path)
+            elif slot == "metric":
+                self.metric = dict(state[key]) if isinstance(state[key], dict) else {"metric": state[key]}
+            elif slot == "optimizer" and self.optimizer is not None:
+                self.optimizer.load_state_dict(state[key])
+            elif slot == "scheduler" and self.optimizer is not None:
+                sd = state[key]
+                self.gamma = sd.get("gamma", getattr(self, "gamma", 1.0))
+                if sd.get("base_lrs"):
+                    self.base_lr = sd["base_lrs"][0]
+                if sd.get("_last_lr"):
+                    self.optimizer.set_lr(sd["_last_lr"][0])
+        self.current_iteration = state["iteration"] + 1 if "iteration" in state else 0
         self.epoch_n = state.get("epoch_n", 0)
-        self.current_iteration = state.get("iteration", 0)
-        self.logger.info("loaded %d/%d tensors from %s", len(ok), len(own), path)
+        return state
 
     def to_device(self, scans):
         return runner.batch_to_device(host_batch(scans), pos_enc_dim=self.pos_enc_dim, device=self.device)
@@ -143,6 +188,7 @@ class _Runner:
 
 class GCNTrain(_Runner):
     """GCNTrain.run / .train (job_runner.py:1350-1416): epochs × scan batches × GCN_STEPS full-batch steps."""
+    _reload_in_base = False
 
     def __init__(self, settings=None, **kw):
         super().__init__(settings, **kw)
@@ -150,10 +196,18 @@ class GCNTrain(_Runner):
         self.model.set_gcn_only()
         opt_kw = dict(s.OPTIMIZER)
         if not opt_kw.pop("method", "torch.optim.SGD").endswith("SGD"):
-            raise SpgnnError("only torch.optim.SGD (momentum) is implemented for the device optimiser")
-        self.optimizer = runner.FlatSGD(self.model.parameters(), lr=opt_kw.get("lr", 1e-4),
-                                        momentum=opt_kw.get("momentum", 0.0))
-        self.gamma = dict(s.SCHEDULER).get("gamma", 1.0)
+            raise SpgnnError("only torch.optim.SGD is implemented for the device optimiser")
+        unknown = set(opt_kw) - {"lr", "momentum", "dampening", "weight_decay", "nesterov"}
+        if unknown:          # e.g. 'groups', 'maximize', 'foreach': refuse rather than train differently in silence
+            raise SpgnnError(f"OPTIMIZER keys {sorted(unknown)} are not supported by the device optimiser")
+        opt_kw.setdefault("lr", 1e-4)
+        self.optimizer = runner.FlatSGD(self.model.parameters(), **opt_kw)
+        self.base_lr = self.optimizer.lr
+        sched_kw = dict(s.SCHEDULER)
+        if not sched_kw.pop("method", "torch.optim.lr_scheduler.ExponentialLR").endswith("ExponentialLR"):
+            raise SpgnnError("only torch.optim.lr_scheduler.ExponentialLR is implemented")
+        self.gamma = sched_kw.get("gamma", 1.0)
+        self.reload_model_from_cache()                # after the optimiser exists, so its state can be restored
         uids = list(self.source.uids)
         n_val = max(1, len(uids) // 10) if len(uids) > 1 else 0
         self.val_uids, self.tr_uids = uids[:n_val], uids[n_val:] or uids
@@ -245,6 +299,7 @@ def branch_accuracy(decision, y):
 
 class GCNTest(_Runner):
     """GCNTest.run (job_runner.py:840-911): one graph at a time → logits → softmax → per-class arg-max node."""
+    _always_reload = True
 
     def run(self, uids=None):
         self.model.eval()

@@ -17,6 +17,39 @@ ACT = {None: 0, "none": 0, "elu": 1, "tanh": 2, "relu": 3, "leaky_relu": 4}
 # 2 = planes + TMA-fed tcgen05 (csrc/gemm_tma.cu)
 GEMM_MODE = 2
 
+# Test hook (oracle/kinks.py replays it): when a list, every non-smooth decision the path takes is appended in call
+# order — ("sign", bool mask: pre-activation of a LeakyReLU / ReLU > 0), ("argmax", source node of every max-pooled
+# element), ("drop", dropout mask already scaled by 1/(1-p)) — so a checker can take the same branches and compare
+# gradients exactly, in train mode too.  None (production): no extra work.
+KINK_TRACE = None
+
+
+def tracing():
+    return KINK_TRACE is not None
+
+
+def trace(kind, value):
+    KINK_TRACE.append((kind, value.detach()))
+
+
+def drop_mask(rows, cols, p, seed, device):
+    """The mask ``concat_dropout`` / attention dropout applies for (p, seed): u01(seed, row*cols + col) >= p."""
+    ones = torch.ones(rows, cols, dtype=torch.float32, device=device)
+    return ConcatDropoutFn.apply(ones, None, float(p), seed)[:, :cols].contiguous()
+
+
+def trace_gat(graph, el, er, attn_p, attn_seed):
+    """GATConv's decisions: LeakyReLU branch of every attention logit and the attention-dropout mask, in DGL edge
+    order ([E, H, 1], the shape of DGL's edge data)."""
+    trace("sign", ((el[graph.src] + er[graph.dst]) > 0).unsqueeze(-1))
+    if attn_p > 0.0:
+        H = el.shape[1]
+        slot_mask = drop_mask(graph.num_edges, H, attn_p, attn_seed, el.device)      # in-CSC slot order
+        edge_mask = torch.empty_like(slot_mask)
+        edge_mask[graph.in_eid.long()] = slot_mask
+        trace("drop", edge_mask.unsqueeze(-1))
+
+
 _seed_state = {"seed": 0x5350474E, "counter": 0}
 
 
@@ -230,6 +263,11 @@ class MlpDropFn(Function):
         y1 = stack.planes_linear(P0, W0, b0.contiguous() if b0 is not None else None, act, float(slope))
         P1 = stack.split_planes(y1, float(p), seed)
         y2 = stack.planes_linear(P1, W3, b3.contiguous() if b3 is not None else None, act, float(slope))
+        if tracing():
+            if p > 0.0:
+                trace("drop", (stack.split_planes(torch.ones_like(y1), float(p), seed).float() > 0).float() * (1.0 / (1.0 - p)))
+            trace("sign", y1 > 0)
+            trace("sign", y2 > 0)
         ctx.planes = (P0, P1)
         ctx.save_for_backward(W0, W3, y1, y2)
         ctx.cfg = (act, float(slope), float(p), seed, b0 is not None, b3 is not None)
@@ -274,9 +312,14 @@ def mlp_drop(x, W0, b0, W3, b3, act="leaky_relu", slope=0.01, p=0.0):
 
 
 def linear(x1, W, bias=None, act=None, slope=0.0, x2=None):
+    code = act_code(act)
     if GEMM_MODE == 2:
-        return PlanesLinearFn.apply(x1, x2, W, bias, act_code(act), slope)
-    return LinearFn.apply(x1, x2, W, bias, act_code(act), slope)
+        out = PlanesLinearFn.apply(x1, x2, W, bias, code, slope)
+    else:
+        out = LinearFn.apply(x1, x2, W, bias, code, slope)
+    if tracing() and code in (ACT["relu"], ACT["leaky_relu"]):
+        trace("sign", out > 0)          # the activation is fused; sign(out) == sign(pre-activation)
+    return out
 
 
 class ConcatDropoutFn(Function):
@@ -311,7 +354,10 @@ def concat_dropout(x1, x2, p, training):
     p = float(p) if training else 0.0
     if p == 0.0 and x2 is None:
         return x1
-    return ConcatDropoutFn.apply(x1, x2, p, next_seed())
+    seed = next_seed()
+    if tracing() and p > 0.0:
+        trace("drop", drop_mask(x1.shape[0], x1.shape[1] + (x2.shape[1] if x2 is not None else 0), p, seed, x1.device))
+    return ConcatDropoutFn.apply(x1, x2, p, seed)
 
 
 class BiasActFn(Function):
@@ -400,6 +446,8 @@ class GatAggFn(Function):
                           N, H, F, ptr(out), out.stride(0), ptr(att), stream(),
                           _key=("bytes", 4.0 * N * (HF + (HF if res_mode == 1 else 0) + 2 * H + (F if mean_heads else HF))
                                 + 4.0 * (N + 1) + 4.0 * graph.num_edges))
+        if tracing():
+            trace_gat(graph, Y[:, el_off:el_off + H], Y[:, er_off:er_off + H], float(drop_p), seed)
         ctx.save_for_backward(Y, xr, b, out if not mean_heads else None, att)
         ctx.graph = graph
         ctx.cfg = (H, F, res_mode, act, float(neg_slope), int(mean_heads), float(drop_p), seed, res_off, el_off, er_off)
@@ -490,6 +538,8 @@ class MaxPoolFn(Function):
         lib().sage_maxpool_fwd(ptr(m), m.stride(0), ptr(graph.in_ptr), ptr(graph.in_src), ptr(out), out.stride(0),
                                ptr(arg), n_dst, F, stream(),
                                _key=("bytes", 4.0 * F * (n_src + 2 * n_dst) + 4.0 * (n_dst + 1) + 4.0 * graph.num_edges))
+        if tracing():
+            trace("argmax", torch.where(arg >= 0, graph.in_src.long()[arg.clamp(min=0).long()], arg.long()))
         ctx.save_for_backward(arg)
         ctx.graph, ctx.n_src = graph, n_src
         return out

@@ -17,15 +17,21 @@ CLASS_WEIGHTS_22 = [0.2] + [0.8] * 21      # exp_settings/st_pgat_spgnn_3.py:70-
 
 
 class FlatSGD:
-    """torch.optim.SGD(momentum) semantics over ONE flat fp32 bucket: parameters are views into one contiguous
-    buffer and a step is one multi-tensor gather of the gradients into a second one, one all-reduce (when
-    world_size > 1) and one fused update kernel.  ``zero_grad`` drops the gradients (``p.grad = None``), so autograd
-    hands over each parameter's gradient without an accumulation kernel per parameter — at the reference's own batch
-    size (64 trees) a step is launch-bound and those ~40 tiny kernels are a tenth of it."""
+    """torch.optim.SGD semantics (momentum, dampening, weight_decay, nesterov; the reference builds
+    ``torch.optim.SGD(model.parameters(), **settings.OPTIMIZER)``, job_runner.py:239-249) over ONE flat fp32 bucket:
+    parameters are views into one contiguous buffer and a step is one multi-tensor gather of the gradients into a
+    second one, one all-reduce (when world_size > 1) and one fused update kernel.  ``zero_grad`` drops the gradients
+    (``p.grad = None``), so autograd hands over each parameter's gradient without an accumulation kernel per
+    parameter — at the reference's own batch size (64 trees) a step is launch-bound and those ~40 tiny kernels are
+    a tenth of it.  As in torch, a parameter whose ``grad`` is None is skipped entirely (no momentum-only update, no
+    weight decay) and its momentum buffer starts at the first gradient it receives."""
 
-    def __init__(self, params, lr, momentum=0.9, process_group=None):
+    def __init__(self, params, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, process_group=None):
         self.params = [p for p in params if p.requires_grad]
         self.lr, self.momentum = float(lr), float(momentum)
+        self.dampening, self.weight_decay, self.nesterov = float(dampening), float(weight_decay), bool(nesterov)
+        if self.nesterov and (self.momentum <= 0.0 or self.dampening != 0.0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")        # torch's own check
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         n = sum(p.numel() for p in self.params)
@@ -33,15 +39,17 @@ class FlatSGD:
         self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.buf = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.g_views = []
+        self.g_views, self.offsets = [], []
         o = 0
         for p in self.params:
             k = p.numel()
             self.flat_p[o:o + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + k].view_as(p.data)
             self.g_views.append(self.flat_g[o:o + k].view_as(p.data))
+            self.offsets.append((o, k))
             p.grad = None
             o += k
+        self.has_buf = [False] * len(self.params)       # momentum buffer initialised (torch: state['momentum_buffer'])
         self.steps = 0
         self.numel = n
 
@@ -50,38 +58,85 @@ class FlatSGD:
             p.grad = None
 
     def _gather(self):
-        """p.grad of every parameter -> its slot of the flat bucket (one multi-tensor copy); parameters that got no
-        gradient contribute zeros.  Afterwards p.grad IS the slot, so callers see the (reduced) values."""
-        dst, src = [], []
-        missing = False
-        for p, v in zip(self.params, self.g_views):
+        """p.grad of every parameter -> its slot of the flat bucket (one multi-tensor copy).  Returns the list of
+        parameters that have a gradient; afterwards their p.grad IS the slot, so callers see the (reduced) values."""
+        dst, src, live, dead = [], [], [], []
+        for i, (p, v) in enumerate(zip(self.params, self.g_views)):
             g = p.grad
             if g is None:
-                missing = True
-            elif g.data_ptr() != v.data_ptr():
+                dead.append(v)
+                continue
+            live.append(i)
+            if g.data_ptr() != v.data_ptr():
                 dst.append(v)
                 src.append(g)
-        if missing:
-            self.flat_g.zero_()
+        if dead:
+            torch._foreach_zero_(dead)                  # absent gradients contribute zeros to the all-reduce
         if dst:
             if hasattr(torch, "_foreach_copy_"):
                 torch._foreach_copy_(dst, src)
             else:
                 for d, g in zip(dst, src):
                     d.copy_(g)
-        for p, v in zip(self.params, self.g_views):
-            p.grad = v
+        for i in live:
+            self.params[i].grad = self.g_views[i]
+        return live
+
+    def _runs(self, live):
+        """Maximal contiguous ranges of the bucket whose parameters are live and share the first-step flag."""
+        runs = []
+        for i in live:
+            o, k = self.offsets[i]
+            first = not self.has_buf[i]
+            if runs and runs[-1][0] + runs[-1][1] == o and runs[-1][2] == first:
+                runs[-1] = (runs[-1][0], runs[-1][1] + k, first)
+            else:
+                runs.append((o, k, first))
+            self.has_buf[i] = True
+        return runs
 
     def step(self):
-        self._gather()
+        live = self._gather()
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
-        lib().sgd_momentum(ptr(self.flat_p), ptr(self.flat_g), ptr(self.buf), self.numel, self.lr, self.momentum, 1.0,
-                           int(self.steps == 0), stream())
+        esz = 4
+        for o, k, first in self._runs(live):
+            lib().sgd_step(self.flat_p.data_ptr() + o * esz, self.flat_g.data_ptr() + o * esz,
+                           self.buf.data_ptr() + o * esz, k, self.lr, self.momentum, self.dampening, self.weight_decay,
+                           int(self.nesterov), 1.0, int(first), stream())
         self.steps += 1
 
     def set_lr(self, lr):
         self.lr = float(lr)
+
+    # ---- torch.optim.SGD-shaped state (job_runner.py:341 saves optimizer.state_dict() under "optimizer_dict")
+    def state_dict(self):
+        state = {}
+        for i, (o, k) in enumerate(self.offsets):
+            if self.has_buf[i] and self.momentum != 0.0:
+                state[i] = {"momentum_buffer": self.buf[o:o + k].view_as(self.params[i].data).detach().cpu().clone()}
+        group = dict(lr=self.lr, momentum=self.momentum, dampening=self.dampening, weight_decay=self.weight_decay,
+                     nesterov=self.nesterov, params=list(range(len(self.params))))
+        return {"state": state, "param_groups": [group], "steps": self.steps}
+
+    def load_state_dict(self, sd):
+        group = sd["param_groups"][0]
+        self.lr = float(group.get("lr", self.lr))
+        self.momentum = float(group.get("momentum", self.momentum))
+        self.dampening = float(group.get("dampening", self.dampening))
+        self.weight_decay = float(group.get("weight_decay", self.weight_decay))
+        self.nesterov = bool(group.get("nesterov", self.nesterov))
+        self.has_buf = [False] * len(self.params)
+        self.buf.zero_()
+        for i, st in sd.get("state", {}).items():
+            i = int(i)
+            mb = st.get("momentum_buffer") if isinstance(st, dict) else None
+            if mb is None or i >= len(self.params) or mb.numel() != self.offsets[i][1]:
+                continue
+            o, k = self.offsets[i]
+            self.buf[o:o + k].copy_(mb.reshape(-1).to(self.buf.device, torch.float32))
+            self.has_buf[i] = True
+        self.steps = int(sd.get("steps", max(self.steps, 1 if any(self.has_buf) else 0)))
 
 
 def _allreduce_sums(group=None):

@@ -272,6 +272,9 @@ def _forward(plan: StackPlan, graph, ext, packed, biases, head, training, keep):
     for i, L in enumerate(plan.layers):
         conv = L.conv
         nch = (L.k_in + 3) // 4
+        if ops.tracing() and pdrop[i] > 0.0:          # this layer's feat_drop mask over its concatenated input
+            kept = split_planes(torch.ones(N, L.k_in, device=dev), pdrop[i], fseed[i], nch, 0).float() > 0
+            ops.trace("drop", kept.float() * (1.0 / (1.0 - pdrop[i])))
         ins = []
         for t, off in zip(L.inputs, L.in_offs):
             key = (t, vkey[i])
@@ -321,6 +324,8 @@ def _forward(plan: StackPlan, graph, ext, packed, biases, head, training, keep):
         d.bias = ptr(b)
         d.attn_drop_p = conv.attn_drop_p if training else 0.0
         d.attn_seed = aseed[i]
+        if ops.tracing():
+            ops.trace_gat(graph, Y[:, L.el_off:L.el_off + L.H], Y[:, L.er_off:L.er_off + L.H], d.attn_drop_p, aseed[i])
         att = torch.empty(E, L.H, dtype=torch.float32, device=dev)
         d.att = ptr(att)
         out32 = ops.empty_padded(N, L.width, dev) if is_out else None
@@ -392,6 +397,8 @@ def _wide_forward(L, graph, ins, W, bias, conv, training, aseed, want_out, want_
     XA = Planes(N, (H + 1) * kp, dev)
     att = torch.empty(E, H, dtype=torch.float32, device=dev)
     d = _wide_desc(L, graph, conv, training, aseed, XA, kp, eler, att)
+    if ops.tracing():
+        ops.trace_gat(graph, eler[:, :H], eler[:, H:2 * H], d.attn_drop_p, aseed)
     d.X1, d.ldx1, d.psx1, d.K1 = ins[0].ptr(), ins[0].ld, ins[0].ps, ins[0].cols
     if len(ins) > 1:
         d.X2, d.ldx2, d.psx2, d.K2 = ins[1].ptr(), ins[1].ld, ins[1].ps, ins[1].cols

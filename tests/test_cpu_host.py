@@ -174,12 +174,19 @@ def test_flat_sgd_gathers_gradients_into_one_bucket():
     net[1](net[0](torch.randn(4, 5))).square().sum().backward()
     ref = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in net.parameters()]
     opt.flat_g.fill_(7.0)                                   # stale content must not survive
-    opt._gather()
+    live = opt._gather()
+    assert live == [0, 1, 2, 3]                             # the unused Linear(7, 1) has no gradient: skipped like torch
     assert torch.equal(opt.flat_g, torch.cat([r.reshape(-1) for r in ref]))
-    for p, v in zip(net.parameters(), opt.g_views):
-        assert p.grad.data_ptr() == v.data_ptr()
-    opt._gather()                                           # idempotent once p.grad is the slot
+    for i, (p, v) in enumerate(zip(net.parameters(), opt.g_views)):
+        assert (p.grad.data_ptr() == v.data_ptr()) if i in live else (p.grad is None)
+    assert opt._gather() == live                            # idempotent once p.grad is the slot
     assert torch.equal(opt.flat_g, torch.cat([r.reshape(-1) for r in ref]))
+    # update ranges: one contiguous run over the four live parameters, first step; the skipped ones keep no buffer
+    assert opt._runs(live) == [(0, sum(b.numel() for b in before[:4]), True)]
+    assert opt.has_buf == [True] * 4 + [False] * 2
+    assert opt._runs([0, 1, 3]) == [(0, 18, False), (24, 2, False)]
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["params"] == list(range(6)) and sd["param_groups"][0]["lr"] == 0.1
     opt.zero_grad()
     assert all(p.grad is None for p in net.parameters())
 

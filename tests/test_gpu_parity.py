@@ -7,12 +7,18 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (FULL_MODELS, TINY_MODELS, golden_graph_inputs, golden_state_dict, load_golden, rel_err)
+from helpers import (FULL_MODELS, TINY_MODELS, assert_grads_match, golden_graph_inputs, golden_state_dict, load_golden,
+                     oracle_fp64, rel_err, rel_err_elementwise, replay, traced)
 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4          # north_star tolerance for fp32 logits / encodings
-GRAD_TOL = 2e-4     # gradients: same bar, a little head-room for the split-order of the weight-gradient reduction
+GRAD_TOL = 2e-4     # gradients vs the fp64 oracle, relative to the parameter's largest entry (eval mode)
+# Train mode: attention dropout rescales the surviving attention weights by 1/(1-p) and zeroes others, which makes the
+# softmax backward (da - sum a da) cancel harder; the projection's split-bf16 operands carry 2^-18 = 3.8e-6 per value
+# (60x the rounding of an fp32 FMA chain, 1/130 of the TF32 the reference's torch 1.9 used by default) and the
+# cancellation amplifies it to 2-4e-4 on the attention vectors of the dropped layers (measured, branches pinned).
+TRAIN_GRAD_TOL = 5e-4
 
 
 @pytest.fixture(scope="module")
@@ -177,16 +183,20 @@ def _full_cases():
 
 @pytest.mark.parametrize("name,mode", _full_cases())
 def test_full_width_forward_backward_vs_oracle(mods, name, mode, monkeypatch):
-    """exp_settings widths, 6 ragged trees, eval-mode forward + all parameter gradients vs the CPU oracle.
+    """exp_settings widths, 6 ragged trees, eval-mode forward + all parameter gradients vs the CPU oracle, in every
+    GEMM mode and at the SAME bar (1e-4 outputs, 2e-4 gradients) for every model family.
 
-    GAT-family models are checked end to end with the tensor-core projections.  SAGE's max-pool and GIN's / SAGE's
-    ReLU-type kinks make the GRADIENT a discontinuous function of the forward values: a 1e-6 perturbation of two
-    nearly tied neighbours re-routes one sample's gradient (a ~1/sqrt(N) change of that weight row).  For those the
-    strict gradient bar is applied with the fp32 SIMT projections (mode 0), and with tensor cores (modes 1, 2) the
-    forward outputs keep the strict bar while gradients get a 3e-2 bar."""
+    The gradient of a LeakyReLU / ReLU / max is a discontinuous function of the forward values: an attention logit,
+    an MLP pre-activation or a pair of pooled neighbours within rounding distance of the kink / the tie takes one
+    branch on the device and the other in the oracle, and a whole gradient row moves (this is what the 3e-2 bar of
+    round 1 and the "in-degree > 4" xfail were hiding: scripts/deg5_bisect.py shows every kernel exact on those
+    graphs).  The device therefore records the branch it took at every such decision (ops.KINK_TRACE) and the oracle
+    replays it (oracle/kinks.py), verifying that each decision it would have taken differently sat within 1e-4 of
+    the kink.  With the branches pinned the two implementations compute the same function and are compared
+    exactly."""
     kind, cfg = FULL_MODELS[name]
-    monkeypatch.setattr(mods["ops"], "GEMM_MODE", mode)
-    grad_tol = GRAD_TOL if (mode == 0 or kind in ("gat", "spgnn")) else 3e-2
+    ops = mods["ops"]
+    monkeypatch.setattr(ops, "GEMM_MODE", mode)
     scans = _scan_dicts(mods, 1000, 6, ragged=True)
     pos = None
     if kind == "spgnn":
@@ -211,34 +221,27 @@ def test_full_width_forward_backward_vs_oracle(mods, name, mode, monkeypatch):
     cw = torch.tensor([0.2] + [0.8] * 21)
     mask = torch.from_numpy(np.concatenate([s["labels"] for s in scans]) != 0) | (torch.rand(y.numel(), generator=torch.Generator().manual_seed(1)) < 0.15)
 
-    ref = onet(og)
-    loss_ref = mods["om"].cross_entropy_masked(ref[0], y, mask, cw)
-    loss_ref.backward()
-    out = net(g)
-    loss = mods["ops"].masked_cross_entropy(out[0], y.cuda(), cw.cuda(), mask=mask.cuda())
+    out, rec = traced(ops, lambda: net(g))
+    loss = ops.masked_cross_entropy(out[0], y.cuda(), cw.cuda(), mask=mask.cuda())
     loss.backward()
+    ref, tape = replay(rec, lambda: onet(og))                 # fp32, as DGL computes: the reference for the outputs
+    loss_ref = mods["om"].cross_entropy_masked(ref[0], y, mask, cw)
+    onet64, og64 = oracle_fp64(onet, og)                      # fp64: the reference for the gradients
+    ref64, _ = replay(rec, lambda: onet64(og64))
+    mods["om"].cross_entropy_masked(ref64[0], y, mask, cw.double()).backward()
 
     for j in range(len(ref)):
         assert rel_err(out[j].detach().cpu(), ref[j].detach()) < TOL, (name, "output", j)
+        # element-wise: logits against 1e-4 x (|ref| + max|ref| / 4); the embeddings (tanh / ELU outputs, whose
+        # pre-activations are larger than the outputs) against 1e-4 x (|ref| + max|ref| / 2)
+        assert rel_err_elementwise(out[j].detach().cpu(), ref[j].detach(), 0.25 if j == 0 else 0.5) < TOL, \
+            (name, "output, element-wise", j)
     assert abs(loss.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
     assert _margin_aware_flips(out[0].detach().cpu(), ref[0].detach(), TOL) == 0
-    dec = mods["ops"].segmented_argmax(out[0].detach(), g).cpu()
+    dec = ops.segmented_argmax(out[0].detach(), g).cpu()
     dec_ref = mods["om"].decide_per_tree(ref[0].detach(), og.batch_num_nodes())
     assert torch.equal(dec, dec_ref)
-    ograds = dict(onet.named_parameters())
-    # Gradients that are analytically ~0 (e.g. d attn_r: the softmax is shift-invariant in er, only the LeakyReLU
-    # kink lets anything through) are pure fp32 cancellation noise in BOTH implementations; they are held to an
-    # absolute floor of 1e-6 x the largest gradient in the model instead of a relative bar against noise.
-    gmax = max(float(q.grad.abs().max()) for q in ograds.values() if q.grad is not None)
-    for k, p in net.named_parameters():
-        r = ograds[k].grad
-        if r is None:
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
-            continue
-        assert p.grad is not None, k
-        abs_err = float((p.grad.cpu().double() - r.double()).abs().max())
-        assert abs_err <= grad_tol * float(r.abs().max()) or abs_err <= 1e-6 * gmax, \
-            (name, k, rel_err(p.grad.cpu(), r), abs_err, gmax)
+    assert_grads_match(net, onet64, GRAD_TOL, (name, mode, f"{tape.flips} of {tape.decisions} decisions pinned"))
 
 
 @pytest.mark.parametrize("name", ["st_gat_3", "st_gat_6_nr", "st_pgat_spgnn_3", "st_pgat_spgnnnl_3"])
@@ -550,64 +553,170 @@ def _random_tree_adj(n, max_children, rng):
     return adj
 
 
-@pytest.mark.parametrize("case", [
-    "tiny_trees",
-    pytest.param("trifurcations", marks=pytest.mark.xfail(
-        strict=False,
-        reason="KNOWN ISSUE (found at the end of round 1, no GPU time left to bisect): with in-degree > 4 the forward and "
-               "the loss match the oracle, but parameter gradients (attn_l, attn_r, res_fc.weight, ...) are off by "
-               "2-3 % (general-degree branch of the chunk backward kernels in gat_layer.cu / gat_wide.cu); "
-               "see DESIGN.md section 7")),
-    "above_384_nodes"])
-def test_gat3_on_edge_case_graphs_vs_oracle(mods, case):
-    """st_gat_3 at full width on graphs outside the per-tree kernels' envelope (degree <= 4, <= 384 nodes, which the
-    synthetic bifurcating trees never leave): single-node and 3-node trees in a batch, airway trees with tri- and
-    quadrifurcations (in-degree up to 6), a tree of 801 nodes.  Forward, loss and parameter gradients vs the oracle."""
-    rng = np.random.default_rng(7)
+def _edge_case_adjs(case, rng):
     if case == "tiny_trees":
-        adjs = [_random_tree_adj(n, 2, rng) for n in (1, 3, 120, 1, 2)]
-    elif case == "trifurcations":
-        adjs = [_random_tree_adj(n, 4, rng) for n in (150, 90)]
-    else:
-        adjs = [_random_tree_adj(801, 2, rng), _random_tree_adj(60, 2, rng)]
+        return [_random_tree_adj(n, 2, rng) for n in (1, 3, 120, 1, 2)]
+    if case == "trifurcations":
+        return [_random_tree_adj(n, 4, rng) for n in (150, 90)]
+    return [_random_tree_adj(801, 2, rng), _random_tree_adj(60, 2, rng)]
+
+
+def _model_pair(mods, name, train):
+    kind, cfg = FULL_MODELS[name]
+    torch.manual_seed(0)
+    onet = mods["om"].GNNNet(kind, cfg)
+    onet.init_like_reference()
+    with torch.no_grad():
+        for k, p in onet.named_parameters():
+            if k.endswith("bias"):
+                p.normal_(0, 0.05)
+    net = getattr(mods["sm"], NET_CLS[kind])(**cfg).cuda()
+    net.load_state_dict(onet.state_dict(), strict=True)
+    onet.train(train)
+    net.train(train)
+    return kind, onet, net
+
+
+def _scans_on(adjs, rng, n_min_anchor=False):
     scans = []
     for a in adjs:
         n = a.shape[0]
         scans.append(dict(adj=a, fvs=np.maximum(rng.standard_normal((n, 1024)), 0).astype(np.float32),
-                          fvs_out=rng.standard_normal((n, 22)).astype(np.float32),
+                          fvs_out=(3 * rng.standard_normal((n, 22))).astype(np.float32),
                           labels=rng.integers(0, 22, n).astype(np.int64)))
-    kind, cfg = FULL_MODELS["st_gat_3"]
-    torch.manual_seed(0)
-    onet = mods["om"].GNNNet(kind, cfg)
-    onet.init_like_reference()
-    onet.eval()
-    net = mods["sm"].GATNet(**cfg).cuda()
-    net.load_state_dict(onet.state_dict(), strict=True)
-    net.eval()
-    og, g = _oracle_batch(mods, scans), _device_batch(mods, scans)
+    return scans
+
+
+def _compare_step(mods, name, scans, train, tag):
+    """One forward + loss + backward of ``name`` on ``scans``: device (decisions recorded) vs oracle (decisions
+    replayed); outputs, loss and every parameter gradient at the parity bar."""
+    ops = mods["ops"]
+    kind, onet, net = _model_pair(mods, name, train)
+    pos = None
+    if kind == "spgnn":
+        pos = [mods["ope"].dist_pos_enc(s["adj"], mods["ope"].anchors_39(s["fvs_out"], s["adj"]))[0] for s in scans]
+    og = _oracle_batch(mods, scans, pos)
+    g = _device_batch(mods, scans, np.concatenate(pos) if pos is not None else None)
     assert torch.equal(g.src.cpu(), og.src) and torch.equal(g.dst.cpu(), og.dst)
-    if case == "trifurcations":
-        assert g.max_degree() > 4
     y = torch.from_numpy(np.concatenate([s["labels"] for s in scans]))
     cw = torch.tensor([0.2] + [0.8] * 21)
     mask = torch.ones(y.numel(), dtype=torch.bool)
-    ref = onet(og)
-    loss_ref = mods["om"].cross_entropy_masked(ref[0], y, mask, cw)
-    loss_ref.backward()
-    out = net(g)
-    loss = mods["ops"].masked_cross_entropy(out[0], y.cuda(), cw.cuda(), mask=mask.cuda())
+    ops.manual_seed(5)
+    out, rec = traced(ops, lambda: net(g))
+    loss = ops.masked_cross_entropy(out[0], y.cuda(), cw.cuda(), mask=mask.cuda())
     loss.backward()
+    ref, tape = replay(rec, lambda: onet(og))                 # fp32 oracle: outputs and loss
+    loss_ref = mods["om"].cross_entropy_masked(ref[0], y, mask, cw)
+    onet64, og64 = oracle_fp64(onet, og)                      # fp64 oracle: gradients
+    ref64, _ = replay(rec, lambda: onet64(og64))
+    mods["om"].cross_entropy_masked(ref64[0], y, mask, cw.double()).backward()
+    if train and kind != "gcn":                       # GraphConv stacks have no dropout
+        assert any(k == "drop" for k, _ in rec), "train mode without a dropout mask on the tape"
     for j in range(len(ref)):
-        assert rel_err(out[j].detach().cpu(), ref[j].detach()) < TOL, (case, j)
+        assert rel_err(out[j].detach().cpu(), ref[j].detach()) < TOL, (tag, j)
     assert abs(loss.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
-    ograds = dict(onet.named_parameters())
-    gmax = max(float(q.grad.abs().max()) for q in ograds.values() if q.grad is not None)
-    bad = []
-    for k, p in net.named_parameters():
-        r = ograds[k].grad
-        if r is None:
-            continue
-        abs_err = float((p.grad.cpu().double() - r.double()).abs().max())
-        if not (abs_err <= GRAD_TOL * float(r.abs().max()) or abs_err <= 1e-6 * gmax):
-            bad.append((k, f"{abs_err:.3e}", f"{float(r.abs().max()):.3e}"))
-    assert not bad, (case, f"gmax {gmax:.3e}", bad)
+    assert_grads_match(net, onet64, TRAIN_GRAD_TOL if train else GRAD_TOL,
+                       (tag, f"{tape.flips} of {tape.decisions} decisions pinned"))
+    return g, tape
+
+
+@pytest.mark.parametrize("train", [False, True])
+@pytest.mark.parametrize("name", ["st_gat_3", "st_pgat_spgnn_3"])
+@pytest.mark.parametrize("case", ["tiny_trees", "trifurcations", "above_384_nodes"])
+def test_edge_case_graphs_vs_oracle(mods, case, name, train):
+    """Full-width GAT-3 and SPGNN-3 on graphs outside the per-tree kernels' envelope (degree <= 4, <= 384 nodes,
+    which the synthetic bifurcating trees never leave): single-node and 3-node trees in a batch, airway trees with
+    tri- and quadrifurcations (in-degree up to 6: general-degree branches of gat_layer.cu / gat_wide.cu), a tree of
+    801 nodes.  Forward, loss and every parameter gradient vs the oracle, eval and train mode (dropout masks and
+    LeakyReLU branches replayed from the device, oracle/kinks.py)."""
+    rng = np.random.default_rng(7)
+    adjs = _edge_case_adjs(case, rng)
+    if name == "st_pgat_spgnn_3":
+        adjs = [a for a in adjs if a.shape[0] >= 21] or [_random_tree_adj(30, 2, rng)]   # 21 distinct anchors per tree
+    g, _ = _compare_step(mods, name, _scans_on(adjs, rng), train, (case, name, train))
+    if case == "trifurcations":
+        assert g.max_degree() > 4
+
+
+def test_random_trees_up_to_six_children_sweep(mods):
+    """Hypothesis-style sweep: random batches of random trees with up to 6 children per node (in-degree up to 8),
+    random sizes on both sides of the per-tree kernels' limits, GAT-3 and SPGNN-3, eval and train."""
+    rng = np.random.default_rng(2026)
+    for trial in range(8):
+        mc = int(rng.integers(2, 7))
+        sizes = [int(rng.integers(21, 420)) for _ in range(int(rng.integers(1, 5)))]
+        adjs = [_random_tree_adj(n, mc, rng) for n in sizes]
+        name = ("st_gat_3", "st_pgat_spgnn_3")[trial % 2]
+        _compare_step(mods, name, _scans_on(adjs, rng), bool((trial // 2) % 2), ("sweep", trial, mc, sizes, name))
+
+
+def test_batch_builder_csc_csr_consistency_above_degree_4(mods):
+    """In-CSC / out-CSR of a batch with in-degree up to 8 (the backward's source side is the only consumer of the
+    out-CSR; the bifurcating synthetic trees never exceed degree 4)."""
+    rng = np.random.default_rng(11)
+    adjs = [_random_tree_adj(n, 6, rng) for n in (150, 90, 33, 301)]
+    g = mods["sg"].batch_from_adjs(adjs)
+    assert g.max_degree() > 4
+    og = _oracle_batch(mods, [dict(adj=a, fvs=np.zeros((a.shape[0], 1), np.float32)) for a in adjs])
+    src, dst = g.src.cpu(), g.dst.cpu()
+    assert torch.equal(src, og.src) and torch.equal(dst, og.dst)
+    in_ptr, in_src, in_eid = g.in_ptr.cpu().long(), g.in_src.cpu().long(), g.in_eid.cpu().long()
+    order = torch.sort(dst, stable=True)[1]
+    assert torch.equal(in_eid, order) and torch.equal(in_src, src[order])
+    assert torch.equal(in_ptr[1:] - in_ptr[:-1], torch.bincount(dst, minlength=g.num_nodes))
+    out_ptr, out_dst, out_slot = g.out_ptr.cpu().long(), g.out_dst.cpu().long(), g.out_slot.cpu().long()
+    assert torch.equal(torch.sort(out_slot)[0], torch.arange(g.num_edges))          # a permutation of the slots
+    owner = torch.repeat_interleave(torch.arange(g.num_nodes), out_ptr[1:] - out_ptr[:-1])
+    assert torch.equal(in_src[out_slot], owner)
+    assert torch.equal(out_dst, dst[in_eid[out_slot]])
+    assert torch.equal(out_ptr[1:] - out_ptr[:-1], torch.bincount(src, minlength=g.num_nodes))
+    assert int((in_ptr[1:] - in_ptr[:-1]).max()) == g.max_degree()
+
+
+@pytest.mark.parametrize("name", sorted(FULL_MODELS))
+def test_train_mode_step_matches_oracle_exactly(mods, name):
+    """The benchmarked configuration (train mode: feature dropout, attention dropout, GIN's MLP dropout) against the
+    oracle with the device's dropout masks injected — the one configuration round 1 only checked statistically."""
+    scans = _scan_dicts(mods, 3000, 4, ragged=True)
+    _compare_step(mods, name, scans, True, ("train", name))
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+@pytest.mark.parametrize("kw", [dict(momentum=0.9), dict(momentum=0.0), dict(momentum=0.9, weight_decay=1e-2),
+                                dict(momentum=0.9, nesterov=True), dict(momentum=0.8, dampening=0.3, weight_decay=5e-3)])
+def test_flat_sgd_matches_torch_optim_sgd(mods, kw):
+    """runner.FlatSGD / spgnn_sgd_step against torch.optim.SGD (the reference's optimiser, job_runner.py:239-249,
+    1919) over 5 steps including step 0 (momentum buffer = first gradient), with an ExponentialLR decay between
+    steps (job_runner.py:1346-1348, gamma 0.9), a parameter that never receives a gradient (torch skips it: no
+    momentum-only drift, no weight decay) and one that receives its first gradient at step 2."""
+    from spgnn_b200 import runner
+    torch.manual_seed(1)
+    shapes = [(37, 19), (19,), (5, 7, 3), (11,), (64, 33)]
+    init = [torch.randn(*s) for s in shapes]
+    ref_p = [torch.nn.Parameter(t.clone().double()) for t in init]
+    dev_p = [torch.nn.Parameter(t.clone().cuda()) for t in init]
+    lr, gamma = 0.05, 0.9
+    ref_opt = torch.optim.SGD(ref_p, lr=lr, **kw)
+    sched = torch.optim.lr_scheduler.ExponentialLR(ref_opt, gamma=gamma)
+    opt = runner.FlatSGD(dev_p, lr=lr, **kw)
+    for step in range(5):
+        ref_opt.zero_grad()
+        opt.zero_grad()
+        for i, (r, d) in enumerate(zip(ref_p, dev_p)):
+            if i == 3 or (i == 2 and step < 2):
+                continue                                   # no gradient: both optimisers must leave it alone
+            g = torch.randn(*shapes[i], generator=torch.Generator().manual_seed(100 * step + i))
+            r.grad = g.double()
+            d.grad = g.cuda()
+        ref_opt.step()
+        opt.step()
+        sched.step()
+        opt.set_lr(opt.lr * gamma)
+        for i, (r, d) in enumerate(zip(ref_p, dev_p)):
+            assert rel_err(d.detach().cpu(), r.detach()) < 2e-6, (kw, step, i)
+    assert torch.equal(dev_p[3].detach().cpu(), init[3])
+    sd = opt.state_dict()
+    assert 3 not in sd["state"] and (bool(sd["state"]) == (kw["momentum"] != 0.0))
+    if kw["momentum"]:
+        for i in (0, 1, 2, 4):
+            assert rel_err(sd["state"][i]["momentum_buffer"], ref_opt.state[ref_p[i]]["momentum_buffer"]) < 2e-6

@@ -55,3 +55,77 @@ def test_other_presets_take_a_training_step(tmp_path, preset):
     losses = tr.train_batch([tr.source(u) for u in tr.source.uids], steps=3)
     assert len(losses) == 3 and np.isfinite(losses).all()
     assert np.isfinite(tr.validate(tr.source.uids[:1]))
+
+
+def test_stage1_pickles_in_the_reference_layout_feed_the_device_batch(tmp_path):
+    """ConvEmbeddingExtractor's pickle (job_runner.py:796-805: ``fvs`` float64 [n,1024], ``adj`` uint8 [n,n],
+    ``labels`` uint8 [n], ``fvs_out`` float64 [n,22] + ref / all_airway / branch_info / meta) written to
+    ``<DB_PATH>/derived/conv_embedding/<uid>.pkl`` and read back through ScanSource → host_batch → the device batch
+    builder: graph, features and labels equal those built straight from the arrays."""
+    import pickle
+    from spgnn_b200 import graph as sg, job_runner, runner, synth
+    from spgnn_b200.settings import Settings
+    scans = synth.make_scans(50, 3, ragged=True)
+    root = tmp_path / "derived" / "conv_embedding"
+    root.mkdir(parents=True)
+    for i, sc in enumerate(scans):
+        n = sc.adj.shape[0]
+        with open(root / f"scan_{i:03d}.pkl", "wb") as fp:
+            pickle.dump({"fvs": sc.fvs.astype(np.float64), "adj": sc.adj.astype(np.uint8),
+                         "labels": sc.labels.astype(np.uint8), "fvs_out": sc.fvs_out.astype(np.float64),
+                         "ref": np.zeros((4, 4, 4), np.uint8), "all_airway": np.zeros((4, 4, 4), np.uint8),
+                         "branch_info": {k: dict(label=int(sc.labels[k])) for k in range(n)},
+                         "meta": {"uid": f"scan_{i:03d}", "spacing": [1.0, 1.0, 1.0]}}, fp)
+    s = Settings("st_pgat_spgnn_3")
+    s.DB_PATH = str(tmp_path)
+    src = job_runner.ScanSource(s)
+    assert src.uids == [f"scan_{i:03d}" for i in range(3)]
+    loaded = [src(u) for u in src.uids]
+    assert loaded[0]["fvs"].dtype == np.float64 and loaded[0]["labels"].dtype == np.uint8
+    hb = job_runner.host_batch(loaded)
+    assert hb.fvs.dtype == torch.float32 and hb.labels.dtype == torch.int64 and hb.adj_cat.dtype == torch.uint8
+    g = runner.batch_to_device(hb, pos_enc_dim=39)
+    ref = sg.batch_from_adjs([sc.adj for sc in scans])
+    assert torch.equal(g.src, ref.src) and torch.equal(g.dst, ref.dst) and torch.equal(g.in_src, ref.in_src)
+    assert torch.equal(g.ndata["fvs"].cpu(), torch.from_numpy(np.concatenate([sc.fvs for sc in scans])))
+    assert torch.equal(g.ndata["y"].cpu(), torch.from_numpy(np.concatenate([sc.labels for sc in scans]).astype(np.int64)))
+    assert g.ndata["pos_enc"].shape == (g.num_nodes, 39)
+
+
+def test_resume_restores_momentum_lr_and_iteration(tmp_path):
+    """save_model / reload_model_from_cache (job_runner.py:298-350): optimizer_dict and scheduler_dict are in the
+    checkpoint; a run resumed with them in RELOAD_DICT_LIST continues with the same momentum buffer, learning rate
+    and iteration + 1; without RELOAD_CHECKPOINT nothing is loaded; a missing checkpoint is not an error."""
+    from spgnn_b200 import job_runner, ops
+    from spgnn_b200.settings import get_callable_by_name
+    torch.manual_seed(0)
+    ops.manual_seed(0)
+    s = _settings(tmp_path, "st_gat_3", scans=3)
+    s.RELOAD_CHECKPOINT = True                      # nothing to reload yet: logged, training starts from scratch
+    tr = get_callable_by_name(s.JOB_RUNNER_CLS)(s)
+    assert tr.current_iteration == 0
+    tr.train_batch([tr.source(u) for u in tr.source.uids], steps=3)
+    tr.optimizer.set_lr(tr.optimizer.lr * tr.gamma)
+    tr.epoch_n = 1
+    path = tr.save_model(metric=0.5)
+    state = torch.load(path, weights_only=False)
+    assert {"iteration", "epoch_n", "model_dict", "optimizer_dict", "scheduler_dict", "metric"} <= set(state)
+    assert len(state["optimizer_dict"]["state"]) == len(tr.optimizer.params)
+
+    s2 = _settings(tmp_path, "st_gat_3", scans=3)
+    s2.RELOAD_CHECKPOINT = True
+    s2.RELOAD_DICT_LIST = ["model_dict", "metric", "optimizer_dict", "scheduler_dict"]
+    tr2 = get_callable_by_name(s2.JOB_RUNNER_CLS)(s2)
+    assert tr2.current_iteration == tr.current_iteration + 1 and tr2.epoch_n == 1
+    assert abs(tr2.optimizer.lr - tr.optimizer.lr) < 1e-12 and tr2.metric == {"metric": 0.5}
+    assert torch.equal(tr2.optimizer.buf, tr.optimizer.buf) and torch.equal(tr2.optimizer.flat_p, tr.optimizer.flat_p)
+    assert all(tr2.optimizer.has_buf)
+
+    s3 = _settings(tmp_path, "st_gat_3", scans=3)   # RELOAD_CHECKPOINT False: a path alone does not reload
+    s3.RELOAD_CHECKPOINT_PATH = path
+    tr3 = get_callable_by_name(s3.JOB_RUNNER_CLS)(s3)
+    assert tr3.current_iteration == 0 and not torch.equal(tr3.optimizer.flat_p, tr.optimizer.flat_p)
+    with pytest.raises(job_runner.SpgnnError):
+        s4 = _settings(tmp_path, "st_gat_3", scans=3)
+        s4.OPTIMIZER = dict(s4.OPTIMIZER, groups={})
+        get_callable_by_name(s4.JOB_RUNNER_CLS)(s4)

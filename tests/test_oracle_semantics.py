@@ -124,3 +124,62 @@ def test_pe_known_answers():
     assert abs(rw[0, 1] - 0.5) < 1e-7             # 2-step return from an end node: 1 · 1/2
     with pytest.raises(ValueError):
         ope.dist_pos_enc(np.eye(4, dtype=np.uint8), [0])
+
+
+def test_kink_tape_replays_decisions_and_flags_real_disagreements():
+    """oracle/kinks.py: with the oracle's OWN decisions on the tape the result is unchanged; a flipped decision that
+    sits on the kink is accepted (and changes the gradient); a flipped decision far from the kink is a violation."""
+    from oracle import kinks
+    rng = np.random.default_rng(3)
+    adj = np.eye(40, dtype=np.uint8)
+    for i in range(1, 40):
+        p = int(rng.integers(0, i))
+        adj[i, p] = adj[p, i] = 1
+    g = dgl_ops.graph_from_adj(adj)
+    torch.manual_seed(0)
+    conv = dgl_ops.GATConv(12, 8, 2, 0.0, 0.0, 0.2, True, F.elu).double()
+    x = torch.randn(40, 12, dtype=torch.float64)
+    z = (x @ conv.fc.weight.t()).view(40, 2, 8)
+    s = ((z * conv.attn_l).sum(-1, keepdim=True)[g.src] + (z * conv.attn_r).sum(-1, keepdim=True)[g.dst]).detach()
+    plain = conv(g, x)
+    with kinks.use(kinks.Tape([("sign", s > 0)])) as tape:
+        same = conv(g, x)
+    assert tape.done() and tape.flips == 0 and not tape.violations and torch.equal(plain, same)
+    # a decision on the kink: move one logit to +-1e-9 by shifting attn... emulate with a hand-made tape instead
+    k = int(s.abs().flatten().argmin())
+    flipped = (s > 0).clone()
+    flipped.view(-1)[k] = ~flipped.view(-1)[k]
+    tol = float(s.abs().flatten()[k] / s.abs().max()) * 1.01
+    with kinks.use(kinks.Tape([("sign", flipped)], tol=tol)) as tape:
+        conv(g, x)
+    assert tape.flips == 1 and not tape.violations
+    with kinks.use(kinks.Tape([("sign", flipped)], tol=tol / 2)) as tape:
+        conv(g, x)
+    assert tape.violations and tape.violations[0][1] == "sign"
+    # tape misuse is loud
+    with pytest.raises(AssertionError):
+        with kinks.use(kinks.Tape([("drop", torch.ones(3))])):
+            conv(g, x)
+    # dropout replay: the injected mask is what the layer applies
+    drop = dgl_ops.GATConv(12, 8, 2, 0.5, 0.0, 0.2, True, None).double()
+    drop.train()
+    mask = (torch.rand(40, 12, generator=torch.Generator().manual_seed(1)) > 0.5).double() * 2.0
+    zd = ((x * mask) @ drop.fc.weight.t()).view(40, 2, 8)
+    sd = ((zd * drop.attn_l).sum(-1, keepdim=True)[g.src] + (zd * drop.attn_r).sum(-1, keepdim=True)[g.dst]).detach()
+    with kinks.use(kinks.Tape([("drop", mask), ("sign", sd > 0)])) as tape:
+        a = drop(g, x)
+    drop.eval()
+    assert tape.done() and torch.allclose(a, drop(g, x * mask))
+    # SAGE max-pool replay: the first-max source per element reproduces the plain result
+    sage = dgl_ops.SAGEConv(12, 6, "pool").double()
+    m = F.relu(sage.fc_pool(x)).detach()
+    arg = torch.full((40, 12), -1, dtype=torch.int64)
+    best = torch.full((40, 12), -np.inf, dtype=torch.float64)
+    for e in range(g.src.numel()):
+        u, v = int(g.src[e]), int(g.dst[e])
+        upd = m[u] > best[v]
+        best[v] = torch.where(upd, m[u], best[v])
+        arg[v] = torch.where(upd, torch.full_like(arg[v], u), arg[v])
+    with kinks.use(kinks.Tape([("sign", sage.fc_pool(x).detach() > 0), ("argmax", arg)])) as tape:
+        b = sage(g, x)
+    assert tape.done() and not tape.violations and torch.allclose(b, sage(g, x))
