@@ -211,9 +211,15 @@ __global__ void reduce_splits_kernel(const float* __restrict__ ws, int64_t split
                                      int64_t K, float* __restrict__ out, int64_t ldo) {
     const int64_t total = N * K;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int64_t z = 0; z < splits; ++z) s += ws[z * split_stride + i];
-        out[(i / K) * ldo + (i % K)] = s;
+        // fixed order: eight interleaved running sums (independent loads in flight), combined pairwise at the end
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int64_t z = 0;
+        for (; z + 8 <= splits; z += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += __ldg(ws + (z + u) * split_stride + i);
+        }
+        for (int u = 0; z < splits; ++z, ++u) s[u] += __ldg(ws + z * split_stride + i);
+        out[(i / K) * ldo + (i % K)] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     }
 }
 

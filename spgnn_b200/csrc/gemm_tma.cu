@@ -590,11 +590,14 @@ struct TnArgs {
     int64_t M; int64_t rows_per_split;
     int npb, nqb;                              // 64-column blocks over the concatenated sources
     int np_tiles, nq_tiles;
+    int flush_kb;                              // k-blocks (of T_BK node rows) accumulated in TMEM between two drains
+    int chunks_per_split;                      // slabs of the workspace per row range (one per drain)
 };
 struct TnShared {
     uint64_t full[T_STAGES];
     uint64_t empty[T_STAGES];
     uint64_t tmem_full;
+    uint64_t tmem_empty;
     uint32_t tmem_base;
 };
 struct Blk { int src, col0, valid; };
@@ -625,6 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_con
             mbar_init(smem_u32(&sh->empty[s]), 1);
         }
         mbar_init(smem_u32(&sh->tmem_full), 1);
+        mbar_init(smem_u32(&sh->tmem_empty), kEpiWarps);
         fence_barrier_init();
     }
     if (warp == 5 && lane == 0) {
@@ -649,12 +653,23 @@ __global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_con
     const int nacc = npb > 2 ? 2 : 1;
     const Blk qlast = blk_of(g.q_cols, qb0 + nqb - 1);
     const int n_mma = 64 * (nqb - 1) + ((qlast.valid + 15) & ~15);
+    // The tensor core adds into its fp32 accumulator with truncation, not round-to-nearest: a chain of n UMMAs drifts
+    // by ~n * 2^-24 of the running sum, always towards zero (measured: dW of 1.23 M rows over 9 row ranges, 25 k UMMAs
+    // per accumulator, 4.8e-4 of the largest entry; scripts/fullsize_precision.py).  The accumulators are therefore
+    // drained every flush_kb k-blocks (8192 node rows = 1536 UMMAs) into a slab of the workspace of their own (plain
+    // coalesced stores, nothing is read back: a read-modify-write of one slab measured +6 ms per step) and
+    // reduce_splits adds the slabs up in fp32 with round-to-nearest, in a fixed order.
+    const int nchunks = (nkb + g.flush_kb - 1) / g.flush_kb;
 
     if (warp < kEpiWarps) {
         // ===================================================== epilogue: TMEM -> partial sums in the workspace
-        mbar_wait(smem_u32(&sh->tmem_full), 0);
-        tc_fence_after();
-        float* obase = g.out + (int64_t)blockIdx.y * g.split_stride;
+      for (int chunk = 0; chunk < g.chunks_per_split; ++chunk) {
+        float* obase = g.out + ((int64_t)blockIdx.y * g.chunks_per_split + chunk) * g.split_stride;
+        const bool live = chunk < nchunks;          // a short last row range leaves its trailing slabs zero
+        if (live) {
+            mbar_wait(smem_u32(&sh->tmem_full), chunk & 1);
+            tc_fence_after();
+        }
         for (int acc = 0; acc < nacc; ++acc) {
             const int pbi = acc * 2 + (warp >> 1);                 // P block of this warp's 32 lanes
             if (pbi >= npb) continue;
@@ -663,35 +678,56 @@ __global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_con
             const bool pok = pin < pb.valid;
             const int64_t pidx = g.p_off[pb.src] + pb.col0 + pin;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
-            for (int c0 = 0; c0 < n_mma; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-                const Blk qb = blk_of(g.q_cols, qb0 + (c0 >> 6));
-                const int qin = c0 & 63;
-                const int nv = min(16, qb.valid - qin);
-                if (pok && nv > 0) {
-                    const int64_t qidx = g.q_off[qb.src] + qb.col0 + qin;
-                    if (g.transposed) {
-                        float* o = obase + qidx * g.ldo + pidx;
+            // 64 accumulator columns per round: four TMEM loads in flight behind ONE wait (a wait per 16 columns made
+            // a drain of the 512 columns ~12 us, during which the tensor pipe idles)
+            for (int c64 = 0; c64 < n_mma; c64 += 64) {
+                uint32_t v[4][16];
+                if (live) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < nv) o[(int64_t)j * g.ldo] = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
-                    } else {
-                        float* o = obase + pidx * g.ldo + qidx;
+                    for (int u = 0; u < 4; ++u)
+                        if (c64 + u * 16 < n_mma) tmem_ld16(taddr + c64 + u * 16, v[u]);
+                    tmem_ld_wait();
+                }
+                const Blk qb = blk_of(g.q_cols, qb0 + (c64 >> 6));
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < nv) o[j] = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
+                for (int u = 0; u < 4; ++u) {
+                    const int qin = u * 16;
+                    const int nv = min(16, qb.valid - qin);
+                    if (c64 + qin < n_mma && pok && nv > 0) {
+                        const int64_t qidx = g.q_off[qb.src] + qb.col0 + qin;
+                        if (g.transposed) {
+                            float* o = obase + qidx * g.ldo + pidx;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < nv) o[(int64_t)j * g.ldo] = live ? __uint_as_float(v[u][j]) : 0.f;
+                        } else {
+                            float* o = obase + pidx * g.ldo + qidx;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < nv) o[j] = live ? __uint_as_float(v[u][j]) : 0.f;
+                        }
                     }
                 }
             }
         }
+        if (chunk + 1 < nchunks) {              // accumulators drained: the UMMA warp may overwrite them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sh->tmem_empty));
+        }
+      }
     } else if (warp == kEpiWarps) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(n_mma, true);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T_STAGES;
                 const uint32_t sp = (kb / T_STAGES) & 1;
+                const int kin = kb % g.flush_kb;            // position inside the accumulation chunk
+                if (kb > 0 && kin == 0) {
+                    umma_commit(smem_u32(&sh->tmem_full));
+                    mbar_wait(smem_u32(&sh->tmem_empty), ((kb / g.flush_kb) - 1) & 1);
+                    tc_fence_after();
+                }
                 mbar_wait(smem_u32(&sh->full[s]), sp);
                 tc_fence_after();
                 const uint32_t p_base = smem_base + s * T_STAGE;
@@ -706,14 +742,14 @@ __global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_con
                         const uint32_t ao = p_base + acc * 2 * T_BLK + ko;
                         const uint64_t dah = make_desc(ao, T_BLK, 1024), dal = make_desc(ao + T_BLK / 2, T_BLK, 1024);
                         const uint32_t td = tmem_base + (uint32_t)(acc * 256);
-                        umma_bf16(td, dah, dbh, idesc, (kb | k) != 0);
+                        umma_bf16(td, dah, dbh, idesc, (kin | k) != 0);
                         umma_bf16(td, dah, dbl, idesc, 1);
                         umma_bf16(td, dal, dbh, idesc, 1);
                     }
                 }
                 umma_commit(smem_u32(&sh->empty[s]));
             }
-            umma_commit(smem_u32(&sh->tmem_full));   // with nkb == 0 nothing is pending: arrives immediately
+            if (nkb > 0) umma_commit(smem_u32(&sh->tmem_full));
         }
     } else if (lane == 0) {
         const uint32_t tx = (uint32_t)(npb + nqb) * T_BLK;
@@ -1173,9 +1209,26 @@ TnPlan tn_plan(int64_t M, int64_t N, int64_t K1, int64_t K2) {
 }
 }  // namespace
 
+// node rows accumulated in TMEM between two drains of the accumulators (see tn_planes_kernel); SPGNN_TN_FLUSH_ROWS
+// overrides it for experiments (0 = never drain: the round-1 behaviour)
+static int tn_flush_kb() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("SPGNN_TN_FLUSH_ROWS");
+        long rows = e ? atol(e) : 8192;
+        cached = rows <= 0 ? (1 << 30) : (int)((rows + T_BK - 1) / T_BK);
+    }
+    return cached;
+}
+
+static int64_t tn_chunks_per_split(const TnPlan& t) {
+    const int64_t c = ceil_div(ceil_div(t.rows, T_BK), tn_flush_kb());
+    return c < 1 ? 1 : c;
+}
+
 extern "C" int64_t spgnn_planes_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K1, int64_t K2) {
     const TnPlan t = tn_plan(M, N, K1, K2);
-    return t.splits * N * (K1 + K2) * (int64_t)sizeof(float) + 256;
+    return t.splits * tn_chunks_per_split(t) * N * (K1 + K2) * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int64_t spgnn_planes_linear_bwd_weight_plan(int64_t M, int64_t N, int64_t K1, int64_t K2, int32_t* out,
@@ -1234,9 +1287,11 @@ extern "C" int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, 
     a.out = reinterpret_cast<float*>(((uintptr_t)ws + 127) & ~(uintptr_t)127);
     a.ldo = Kt; a.split_stride = N * Kt; a.M = M; a.rows_per_split = t.rows;
     a.npb = t.npb; a.nqb = t.nqb; a.np_tiles = t.np_tiles; a.nq_tiles = t.nq_tiles;
+    a.flush_kb = tn_flush_kb();
+    a.chunks_per_split = (int)tn_chunks_per_split(t);
     dim3 grid((unsigned)(t.np_tiles * t.nq_tiles), (unsigned)t.splits);
     tn_planes_kernel<<<grid, kThreads, T_SMEM, st>>>(maps, a);
     SPGNN_LAUNCH_OK();
-    reduce_splits(a.out, t.splits, N, Kt, dW, lddw, st);
+    reduce_splits(a.out, t.splits * a.chunks_per_split, N, Kt, dW, lddw, st);
     return SPGNN_OK;
 }
