@@ -420,6 +420,34 @@ int spgnn_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, fl
                    float weight_decay, int nesterov, float grad_scale, int first_step, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Wire format of a scan batch (host loader -> device batch builder; replaces the dense per-scan H2D copies of
+ * job_runner.py:1872-1875).  Lossless: the device decodes into the tensors the dense path builds, bit for bit.
+ *   zero-suppressed rows: mask [rows, ceil(cols/32)] uint32 (bit b of word w: the fp32 BIT PATTERN of column 32w+b
+ *                         is non-zero), vals = the non-zero values in row-major order, row_off int64 [rows + 1].
+ *     spgnn_host_pack_rows_count : HOST code (no CUDA call): fills row_off, returns the number of values (-1: error).
+ *     spgnn_host_pack_rows_fill  : HOST code: fills mask and vals.  threads <= 0: all hardware threads.
+ *     spgnn_unpack_rows          : device: out fp32 [rows, ldo] (every column < cols written).
+ *   edge lists: off-diagonal non-zeros of each scan's adjacency in row-major order (DGL edge order) as int32 LOCAL
+ *               (src, dst); ne_off int64 [B + 1] = prefix of the per-scan counts.
+ *     spgnn_edges_expand         : device: the int64 LOCAL edge lists spgnn_batch_build takes, with the N self
+ *                                  loops appended last per graph (job_runner.py:1800), and n_edges int64 [B].
+ * ---------------------------------------------------------------------------------- */
+int64_t spgnn_host_pack_rows_count(const float* x, int64_t ldx, int64_t rows, int64_t cols, int64_t* row_off, int threads);
+int spgnn_host_pack_rows_fill(const float* x, int64_t ldx, int64_t rows, int64_t cols, const int64_t* row_off,
+                              uint32_t* mask, float* vals, int threads);
+/* HOST code: dense adjacency blocks (uint8 [n_g, n_g], concatenated; job_runner.py:797 'adj') -> the int32 edge lists
+ * above.  _count fills ne_off [B + 1] and returns the number of edges (-1: error); _fill writes them and the batch's
+ * largest in-/out-degree INCLUDING the self loop the device appends. */
+int64_t spgnn_host_adj_edges_count(const uint8_t* adj_cat, const int64_t* n_nodes, int64_t B, int64_t* ne_off, int threads);
+int spgnn_host_adj_edges_fill(const uint8_t* adj_cat, const int64_t* n_nodes, int64_t B, const int64_t* ne_off,
+                              int32_t* src, int32_t* dst, int32_t* max_degree, int threads);
+int spgnn_unpack_rows(const uint32_t* mask, const float* vals, const int64_t* row_off, int64_t rows, int64_t cols,
+                      float* out, int64_t ldo, void* stream);
+int spgnn_edges_expand(const int32_t* src32, const int32_t* dst32, const int64_t* ne_off, const int64_t* node_off,
+                       int64_t B, int64_t NE, int64_t N, int64_t* src_local, int64_t* dst_local, int64_t* n_edges,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Synthetic airway trees on device (bench input; integer part bit-identical to spgnn_b200/synth.py).
  * ---------------------------------------------------------------------------------- */
 int spgnn_synth_trees(int64_t first_tree, int64_t B, uint32_t seed, int ragged, int64_t k_fixed,

@@ -40,9 +40,12 @@ class Graph:
 
     # ---------------------------------------------------------------- construction
     @classmethod
-    def from_edge_lists(cls, n_nodes, n_edges, src_local, dst_local, max_nodes=None, check=True):
+    def from_edge_lists(cls, n_nodes, n_edges, src_local, dst_local, max_nodes=None, check=True, num_nodes=None,
+                        max_degree=None, zero_in_degree=None):
         """``dgl.batch`` of B graphs given per-graph node/edge counts (int64 [B]) and the concatenated LOCAL
-        edge lists in DGL edge order (int64 [E]); all device tensors."""
+        edge lists in DGL edge order (int64 [E]); all device tensors.  ``num_nodes`` / ``max_degree`` /
+        ``zero_in_degree``: values the caller already knows on the host (a loader that packed the batch): with
+        them and ``check=False`` the build issues no device→host read, so a pipelined caller never stalls."""
         g = cls()
         dev = n_nodes.device
         g.device = dev
@@ -51,7 +54,7 @@ class Graph:
         B = g._bnn.numel()
         g.node_off = device_scan(g._bnn)
         g.edge_off = device_scan(g._bne)
-        N = int(g.node_off[-1].item())
+        N = int(g.node_off[-1].item()) if num_nodes is None else int(num_nodes)
         E = int(src_local.shape[0])
         if check and int(g.edge_off[-1].item()) != E:
             raise SpgnnError("edge list length does not match the per-graph edge counts")
@@ -69,7 +72,7 @@ class Graph:
                           ptr(g.src), ptr(g.dst), ptr(g.node_gid), ptr(g.in_ptr), ptr(g.in_src), ptr(g.in_eid),
                           ptr(g.out_ptr), ptr(g.out_dst), ptr(g.out_slot), ptr(flags), ptr(ws), stream())
         g._flags = flags
-        g.zero_in_degree = g._max_degree = None
+        g.zero_in_degree, g._max_degree = zero_in_degree, max_degree
         if check:
             f = g._read_flags()
             if f[1]:

@@ -75,14 +75,15 @@ class ScanSource:
         return d
 
 
-def host_batch(scans, pin=True):
-    """collate (utils.py:76-84) + the float()/long() casts of job_runner.py:1872-1875, as ONE set of host buffers."""
+def host_batch(scans, pin=True, packed=True):
+    """collate (utils.py:76-84) + the float()/long() casts of job_runner.py:1872-1875, as ONE set of host buffers
+    (``packed``: the lossless wire format of runner.HostBatch / csrc/wire.cu, about half the H2D bytes)."""
     n = [int(np.asarray(s["adj"]).shape[0]) for s in scans]
     adj = torch.from_numpy(np.concatenate([(np.asarray(s["adj"]) != 0).astype(np.uint8).reshape(-1) for s in scans]))
     fvs = torch.from_numpy(np.concatenate([np.asarray(s["fvs"], dtype=np.float32) for s in scans]))
     fvs_out = torch.from_numpy(np.concatenate([np.asarray(s["fvs_out"], dtype=np.float32) for s in scans]))
     labels = torch.from_numpy(np.concatenate([np.asarray(s["labels"]).astype(np.int64).reshape(-1) for s in scans]))
-    return runner.HostBatch(n, adj, fvs, fvs_out, labels, pin=pin)
+    return runner.HostBatch(n, adj, fvs, fvs_out, labels, pin=pin, packed=packed)
 
 
 class _Runner:

@@ -26,8 +26,9 @@ def select_anchors(g, fvs_out=None, pos_enc_dim=39):
     return anchors
 
 
-def distance_pos_enc(g, anchors=None, pos_enc_dim=39, store=True):
-    """pos_enc[n,k] = hops(n, anchor_k) / diameter, fp32 [N, pos_enc_dim]; also returns the per-graph diameters."""
+def distance_pos_enc(g, anchors=None, pos_enc_dim=39, store=True, check=True):
+    """pos_enc[n,k] = hops(n, anchor_k) / diameter, fp32 [N, pos_enc_dim]; also returns the per-graph diameters.
+    ``check=False`` defers the connectivity check (one device→host read) to :func:`check_connected`."""
     if anchors is None:
         anchors = select_anchors(g, pos_enc_dim=pos_enc_dim)
     anchors = anchors.to(torch.int32).contiguous()
@@ -40,12 +41,20 @@ def distance_pos_enc(g, anchors=None, pos_enc_dim=39, store=True):
     # nx shortest paths run v -> anchor: propagate along out-edges (same graph when the adjacency is symmetric)
     lib().pe_dist_init(ptr(g.node_off), ptr(g.out_ptr), ptr(g.out_dst), ptr(anchors), g.batch_size, pos_enc_dim,
                        g.max_nodes, ptr(pe), pe.stride(0), ptr(diam), ptr(flags), ptr(ws), stream())
-    if int(flags.item()):
-        raise SpgnnError("Found infinite path length because the graph is not connected (nx.diameter in the reference)")
+    g._pe_flags = flags
+    if check:
+        check_connected(g)
     if store:
         g.ndata["pos_enc"] = pe
         g.ndata["p"] = pe
     return pe, diam
+
+
+def check_connected(g):
+    """Raises if the last distance_pos_enc of ``g`` met a disconnected graph (nx.diameter raises in the reference)."""
+    flags = getattr(g, "_pe_flags", None)
+    if flags is not None and int(flags.item()):
+        raise SpgnnError("Found infinite path length because the graph is not connected (nx.diameter in the reference)")
 
 
 def rw_pos_enc(g, pos_enc_dim=39, store=True):

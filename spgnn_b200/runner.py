@@ -169,31 +169,100 @@ def infer(net, g):
 
 
 class HostBatch:
-    """A batch of scans in (pinned) host memory, in the stage-1 pickle layout concatenated over scans
-    (job_runner.py:796-805): adj uint8 blocks, fvs fp32 [N,1024], fvs_out fp32 [N,22], labels int64 [N]."""
+    """A batch of scans in (pinned) host memory, ready for the H2D copy of job_runner.py:1872-1875.
 
-    def __init__(self, n_nodes, adj_cat, fvs, fvs_out, labels, pin=True):
+    ``packed=False``: the stage-1 pickle layout concatenated over scans (job_runner.py:796-805): adj uint8 blocks,
+    fvs fp32 [N, fv], fvs_out fp32 [N, 22], labels int64 [N] — 4.5 MB per 301-node scan.
+    ``packed=True`` (default): the lossless wire format of csrc/wire.cu — ``fvs`` zero-suppressed (it is a ReLU
+    output: bit mask + non-zero values), the adjacency as int32 edge lists in DGL edge order, labels as uint8 when
+    they fit — about half the bytes; the device decodes into bit-identical tensors.  Packing is loader work done
+    once per batch when it is read (``pack_threads`` host threads, ``pack_seconds`` records it)."""
+
+    def __init__(self, n_nodes, adj_cat, fvs, fvs_out, labels, pin=True, packed=False, pack_threads=0):
+        import time
         f = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+        self.packed = bool(packed)
         self.n_nodes = f(torch.as_tensor(n_nodes, dtype=torch.int64))
-        self.adj_cat, self.fvs, self.fvs_out, self.labels = f(adj_cat), f(fvs), f(fvs_out), f(labels)
         self.max_nodes = int(self.n_nodes.max())
+        self.fvs_out = f(fvs_out)
+        self.fv_dim = int(fvs.shape[1])
+        self.pack_seconds = 0.0
+        if not self.packed:
+            self.adj_cat, self.fvs, self.labels = f(adj_cat), f(fvs), f(labels)
+            return
+        t0 = time.perf_counter()
+        L = lib()
+        fvs = fvs.contiguous()
+        rows, cols = fvs.shape
+        row_off = torch.empty(rows + 1, dtype=torch.int64)
+        nnz = int(L.host_pack_rows_count(fvs.data_ptr(), fvs.stride(0), rows, cols, row_off.data_ptr(), pack_threads))
+        if nnz < 0:
+            raise RuntimeError("spgnn_host_pack_rows_count failed: " + L.last_error())
+        self.f_row_off = f(row_off)
+        self.f_mask = f(torch.empty(rows, (cols + 31) // 32, dtype=torch.int32))
+        self.f_vals = f(torch.empty(max(nnz, 1), dtype=torch.float32))
+        L.host_pack_rows_fill(fvs.data_ptr(), fvs.stride(0), rows, cols, self.f_row_off.data_ptr(),
+                              self.f_mask.data_ptr(), self.f_vals.data_ptr(), pack_threads)
+        self.f_nnz = nnz
+        # adjacency blocks -> int32 edge lists (row-major order of the off-diagonal non-zeros = DGL edge order)
+        adj_cat = adj_cat.contiguous()
+        nn_ = self.n_nodes.contiguous()
+        B = nn_.numel()
+        e_off = torch.empty(B + 1, dtype=torch.int64)
+        ne = int(L.host_adj_edges_count(adj_cat.data_ptr(), nn_.data_ptr(), B, e_off.data_ptr(), pack_threads))
+        if ne < 0:
+            raise RuntimeError("spgnn_host_adj_edges_count failed: " + L.last_error())
+        self.e_off = f(e_off)
+        self.e_src = f(torch.empty(max(ne, 1), dtype=torch.int32))[:ne]
+        self.e_dst = f(torch.empty(max(ne, 1), dtype=torch.int32))[:ne]
+        md = torch.zeros(1, dtype=torch.int32)
+        L.host_adj_edges_fill(adj_cat.data_ptr(), nn_.data_ptr(), B, self.e_off.data_ptr(), self.e_src.data_ptr(),
+                              self.e_dst.data_ptr(), md.data_ptr(), pack_threads)
+        self.max_degree = int(md.item())              # includes the self loop the device appends to every node
+        small = labels.numel() == 0 or (int(labels.min()) >= 0 and int(labels.max()) < 256)
+        self.labels = f(labels.to(torch.uint8) if small else labels)
+        self.pack_seconds = time.perf_counter() - t0
+
+    def tensors(self):
+        if self.packed:
+            return (self.n_nodes, self.e_off, self.e_src, self.e_dst, self.f_row_off, self.f_mask, self.f_vals,
+                    self.fvs_out, self.labels)
+        return (self.n_nodes, self.adj_cat, self.fvs, self.fvs_out, self.labels)
 
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.n_nodes, self.adj_cat, self.fvs, self.fvs_out, self.labels))
+        return sum(t.numel() * t.element_size() for t in self.tensors())
 
 
 def _upload(hb: HostBatch, dev):
-    return tuple(t.to(dev, non_blocking=True) for t in (hb.n_nodes, hb.adj_cat, hb.fvs, hb.fvs_out, hb.labels))
+    return tuple(t.to(dev, non_blocking=True) for t in hb.tensors())
 
 
-def _assemble(hb: HostBatch, bufs, dev, pos_enc_dim, pe_kind):
-    n_nodes, adj, fvs, fvs_out, labels = bufs
-    n_edges, sl, dl = sg._edges_from_dense(adj, n_nodes, dev)
-    g = sg.Graph.from_edge_lists(n_nodes, n_edges, sl, dl, max_nodes=hb.max_nodes, check=False)
+def _assemble(hb: HostBatch, bufs, dev, pos_enc_dim, pe_kind, defer_checks=False):
+    if hb.packed:
+        n_nodes, e_off, e_src, e_dst, f_row_off, f_mask, f_vals, fvs_out, labels = bufs
+        L = lib()
+        B, N, NE = n_nodes.numel(), int(f_mask.shape[0]), int(e_src.numel())
+        node_off = sg.device_scan(n_nodes)
+        sl = torch.empty(NE + N, dtype=torch.int64, device=dev)
+        dl = torch.empty(NE + N, dtype=torch.int64, device=dev)
+        n_edges = torch.empty(B, dtype=torch.int64, device=dev)
+        L.edges_expand(ptr(e_src), ptr(e_dst), ptr(e_off), ptr(node_off), B, NE, N, ptr(sl), ptr(dl), ptr(n_edges),
+                       stream())
+        fvs = ops.empty_padded(N, hb.fv_dim, dev)
+        L.unpack_rows(ptr(f_mask), ptr(f_vals), ptr(f_row_off), N, hb.fv_dim, ptr(fvs), fvs.stride(0), stream(),
+                      _key=("bytes", 4.0 * hb.f_nnz + 4.0 * N * hb.fv_dim + N * (hb.fv_dim // 8 + 8)))
+        labels = labels.to(torch.int64)
+        # everything the builder would read back is known from packing: no device→host read on this path
+        g = sg.Graph.from_edge_lists(n_nodes, n_edges, sl, dl, max_nodes=hb.max_nodes, check=False, num_nodes=N,
+                                     max_degree=hb.max_degree, zero_in_degree=0)
+    else:
+        n_nodes, adj, fvs, fvs_out, labels = bufs
+        n_edges, sl, dl = sg._edges_from_dense(adj, n_nodes, dev)
+        g = sg.Graph.from_edge_lists(n_nodes, n_edges, sl, dl, max_nodes=hb.max_nodes, check=False)
     g.ndata["fvs"], g.ndata["fvs_out"], g.ndata["y"] = fvs, fvs_out, labels
     if pos_enc_dim:
         if pe_kind == "dist":
-            spe.distance_pos_enc(g, pos_enc_dim=pos_enc_dim)
+            spe.distance_pos_enc(g, pos_enc_dim=pos_enc_dim, check=not defer_checks)
         else:
             g.ndata["pos_enc"] = spe.rw_pos_enc(g, pos_enc_dim)
     return g
@@ -218,6 +287,7 @@ class DeviceBatchLoader:
         self.pos_enc_dim, self.pe_kind = pos_enc_dim, pe_kind
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self._pending = None
+        self._last = None
         self._issue()
 
     def _issue(self):
@@ -240,19 +310,31 @@ class DeviceBatchLoader:
         return self
 
     def __next__(self):
+        if self._last is not None:         # connectivity flag of the PREVIOUS batch: long finished, the read is free
+            if int(self._last.item()):
+                raise RuntimeError("Found infinite path length because the graph is not connected (nx.diameter in "
+                                   "the reference) — in the batch before this one")
+            self._last = None
         if self._pending is None:
             raise StopIteration
         hb, bufs, done = self._pending
         torch.cuda.current_stream(self.dev).wait_event(done)
+        # decode + graph build + positional encoding are queued WITHOUT a device→host read, and only then is the next
+        # batch's copy issued: submitting a multi-GB cudaMemcpyAsync takes the host milliseconds during which kernel
+        # launches crawl (scripts/e2e_timeline.py: 24 ms instead of 4 ms to launch a step) — with the GPU already
+        # holding this batch's build work, that submission costs no GPU idle time
+        g = _assemble(hb, bufs, self.dev, self.pos_enc_dim, self.pe_kind, defer_checks=True)
+        self._last = getattr(g, "_pe_flags", None)
         self._issue()                      # next batch's copy overlaps this batch's graph build + step
-        return _assemble(hb, bufs, self.dev, self.pos_enc_dim, self.pe_kind)
+        return g
 
 
-def host_batch_from_graph(g, pin=True):
+def host_batch_from_graph(g, pin=True, packed=False):
     """Device batch → HostBatch (bench/test helper: produces the host-side inputs of the end-to-end path)."""
     n = g.batch_num_nodes()
     adj_off = sg.device_scan(n * n)
     adj = torch.zeros(int(adj_off[-1].item()), dtype=torch.uint8, device=g.device)
     gid = torch.repeat_interleave(torch.arange(g.batch_size, device=g.device), g.batch_num_edges())
     adj[adj_off[gid] + g.src_local * n[gid] + g.dst_local] = 1
-    return HostBatch(n.cpu(), adj.cpu(), g.ndata["fvs"].cpu(), g.ndata["fvs_out"].cpu(), g.ndata["y"].cpu(), pin=pin)
+    return HostBatch(n.cpu(), adj.cpu(), g.ndata["fvs"].cpu(), g.ndata["fvs_out"].cpu(), g.ndata["y"].cpu(), pin=pin,
+                     packed=packed)

@@ -210,3 +210,59 @@ def test_bench_workloads_and_launch_list_summary():
     first = out.splitlines()[0]
     assert first.startswith("one training step: launches 109"), first
     assert "tn_planes_kernel" in out and "gat_tree_bwd_kernel" in out
+
+
+def test_host_row_packer_round_trips_on_the_cpu():
+    """spgnn_host_pack_rows_* (host code of libspgnn_b200.so, no GPU involved): mask / values / row offsets of
+    zero-suppressed rows reproduce the matrix bit for bit when decoded with numpy; multi-threaded == single-threaded."""
+    import numpy as np
+    import torch
+    from spgnn_b200._lib import lib
+    rng = np.random.default_rng(0)
+    for rows, cols in ((257, 1024), (5, 96), (33, 50), (1, 1)):
+        x = np.maximum(rng.standard_normal((rows, cols)), 0).astype(np.float32)
+        x[0, 0] = -0.0
+        x[:, -3:] = 0.0                                    # rows end in zeros: no write may land in the next row's slots
+        xt = torch.from_numpy(x.copy())
+        res = []
+        for threads in (1, 4):
+            row_off = torch.zeros(rows + 1, dtype=torch.int64)
+            nnz = int(lib().host_pack_rows_count(xt.data_ptr(), cols, rows, cols, row_off.data_ptr(), threads))
+            assert nnz == int((x.view(np.uint32) != 0).sum()) == int(row_off[-1])
+            words = (cols + 31) // 32
+            mask = torch.zeros(rows, words, dtype=torch.int32)
+            vals = torch.full((nnz + 8,), 7.0, dtype=torch.float32)       # guard elements behind the last value
+            lib().host_pack_rows_fill(xt.data_ptr(), cols, rows, cols, row_off.data_ptr(), mask.data_ptr(),
+                                      vals.data_ptr(), threads)
+            assert bool((vals[nnz:] == 7.0).all())
+            res.append((row_off.clone(), mask.clone(), vals[:max(nnz, 1)].clone()))
+        assert all(torch.equal(a, b) for a, b in zip(res[0], res[1]))
+        row_off, mask, vals = (t.numpy() for t in res[0])
+        bits = np.unpackbits(mask.view(np.uint8).reshape(rows, -1), axis=1, bitorder="little")[:, :cols].astype(bool)
+        back = np.zeros((rows, cols), np.float32)
+        back[bits] = vals[:nnz]
+        assert np.array_equal(back.view(np.uint32), x.view(np.uint32))
+        assert np.array_equal(np.diff(row_off), bits.sum(1))
+
+
+def test_packed_host_batch_is_built_without_a_gpu():
+    """runner.HostBatch(packed=True): edge lists in DGL edge order (row-major off-diagonal non-zeros), the batch's
+    largest degree including the self loop, uint8 labels, zero-suppressed features — all host code."""
+    import numpy as np
+    import torch
+    from spgnn_b200 import runner, synth
+    scans = synth.make_scans(3, 6, ragged=True)
+    n = [s.adj.shape[0] for s in scans]
+    hb = runner.HostBatch(n, torch.from_numpy(np.concatenate([s.adj.reshape(-1) for s in scans])),
+                          torch.from_numpy(np.concatenate([s.fvs for s in scans])),
+                          torch.from_numpy(np.concatenate([s.fvs_out for s in scans])),
+                          torch.from_numpy(np.concatenate([s.labels for s in scans]).astype(np.int64)), pin=False, packed=True)
+    srcs, dsts, counts = [], [], [0]
+    for s in scans:
+        r, c = s.adj.nonzero()
+        k = r != c
+        srcs.append(r[k]); dsts.append(c[k]); counts.append(counts[-1] + int(k.sum()))
+    assert np.array_equal(hb.e_src.numpy(), np.concatenate(srcs)) and np.array_equal(hb.e_dst.numpy(), np.concatenate(dsts))
+    assert hb.e_off.tolist() == counts and hb.max_degree == 4 and hb.labels.dtype == torch.uint8
+    fvs = np.concatenate([s.fvs for s in scans])
+    assert hb.f_nnz == int((fvs != 0).sum()) and hb.nbytes() < 0.6 * (fvs.nbytes + sum(k * k for k in n))

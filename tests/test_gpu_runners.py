@@ -82,9 +82,9 @@ def test_stage1_pickles_in_the_reference_layout_feed_the_device_batch(tmp_path):
     assert src.uids == [f"scan_{i:03d}" for i in range(3)]
     loaded = [src(u) for u in src.uids]
     assert loaded[0]["fvs"].dtype == np.float64 and loaded[0]["labels"].dtype == np.uint8
-    hb = job_runner.host_batch(loaded)
+    hb = job_runner.host_batch(loaded, packed=False)
     assert hb.fvs.dtype == torch.float32 and hb.labels.dtype == torch.int64 and hb.adj_cat.dtype == torch.uint8
-    g = runner.batch_to_device(hb, pos_enc_dim=39)
+    g = runner.batch_to_device(job_runner.host_batch(loaded), pos_enc_dim=39)        # the loader's packed wire format
     ref = sg.batch_from_adjs([sc.adj for sc in scans])
     assert torch.equal(g.src, ref.src) and torch.equal(g.dst, ref.dst) and torch.equal(g.in_src, ref.in_src)
     assert torch.equal(g.ndata["fvs"].cpu(), torch.from_numpy(np.concatenate([sc.fvs for sc in scans])))
@@ -129,3 +129,42 @@ def test_resume_restores_momentum_lr_and_iteration(tmp_path):
         s4 = _settings(tmp_path, "st_gat_3", scans=3)
         s4.OPTIMIZER = dict(s4.OPTIMIZER, groups={})
         get_callable_by_name(s4.JOB_RUNNER_CLS)(s4)
+
+
+def test_packed_wire_format_decodes_to_the_dense_batch_bit_for_bit():
+    """runner.HostBatch(packed=True) (csrc/wire.cu: zero-suppressed fvs, int32 edge lists, uint8 labels) → device
+    batch: graph arrays, features (including -0.0 and denormals), labels and positional encoding are bit-identical
+    to the dense stage-1 layout, at about half the bytes; trees with up to 6 children and a 1-node tree included."""
+    import test_gpu_parity as T
+    from spgnn_b200 import job_runner, runner
+    rng = np.random.default_rng(5)
+    adjs = [T._random_tree_adj(n, mc, rng) for n, mc in ((301, 2), (25, 6), (1, 2), (120, 3), (64, 2))]
+    scans = []
+    for a in adjs:
+        n = a.shape[0]
+        f = np.maximum(rng.standard_normal((n, 1024)), 0).astype(np.float32)
+        f[0, :4] = [-0.0, 1e-42, np.float32(3.5), 0.0]                       # negative zero and a denormal survive
+        scans.append(dict(adj=a, fvs=f, fvs_out=rng.standard_normal((n, 22)).astype(np.float32),
+                          labels=rng.integers(0, 22, n).astype(np.uint8)))
+    dense = job_runner.host_batch(scans, packed=False)
+    packed = job_runner.host_batch(scans, packed=True)
+    assert packed.nbytes() < 0.6 * dense.nbytes()
+    gd = runner.batch_to_device(dense, pos_enc_dim=0)
+    gp = runner.batch_to_device(packed, pos_enc_dim=0)
+    for k in ("src", "dst", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_slot", "node_off", "edge_off"):
+        assert torch.equal(getattr(gd, k), getattr(gp, k)), k
+    assert gp.max_degree() == gd.max_degree() > 4
+    assert torch.equal(gd.ndata["fvs"].view(torch.int32), gp.ndata["fvs"].view(torch.int32))       # bit patterns
+    assert torch.equal(gd.ndata["fvs_out"], gp.ndata["fvs_out"]) and torch.equal(gd.ndata["y"], gp.ndata["y"])
+    assert gp.ndata["y"].dtype == torch.int64
+    # an all-zero feature matrix and a dense one
+    for f in (np.zeros((40, 96), np.float32), rng.standard_normal((40, 96)).astype(np.float32)):
+        sc = [dict(adj=T._random_tree_adj(40, 2, rng), fvs=f, fvs_out=np.zeros((40, 22), np.float32),
+                   labels=np.zeros(40, np.int64))]
+        g1 = runner.batch_to_device(job_runner.host_batch(sc, packed=True), pos_enc_dim=0)
+        assert torch.equal(g1.ndata["fvs"].cpu(), torch.from_numpy(f))
+    # through the pipelined loader, with the positional encoding
+    big = [s for s in scans if s["adj"].shape[0] >= 21]
+    a = next(iter(runner.DeviceBatchLoader([job_runner.host_batch(big, packed=True)], pos_enc_dim=39)))
+    b = next(iter(runner.DeviceBatchLoader([job_runner.host_batch(big, packed=False)], pos_enc_dim=39)))
+    assert torch.equal(a.ndata["pos_enc"], b.ndata["pos_enc"]) and torch.equal(a.ndata["fvs"], b.ndata["fvs"])
