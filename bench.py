@@ -406,6 +406,44 @@ def run_ours(args):
         e2e_dense = e2e_measure(hbd, max(3, args.e2e_steps // 3), "dense stage-1 pickle layout")
         del hbd
 
+    # -------- the reference's own regime (TRAIN_BATCH_SIZE = 64 scans, GCN_STEPS = 300 steps on one batch,
+    # job_runner.py:1892-1919; inference one scan at a time, :840-911): launch-bound, so the step is replayed from a
+    # CUDA graph (runner.GraphedTrainStep)
+    small = None
+    if rank == 0 and world == 1 and not args.no_small and B > 64:
+        sb = synth_device.make_batch(first_tree=0, count=64, seed=SEED, ragged=True).graph
+        if pe_dim:
+            spe.distance_pos_enc(sb, pos_enc_dim=pe_dim)
+
+        def timed(fn, n):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n, (time.perf_counter() - t0) / n * 1e3
+
+        eager_ms, eager_wall = timed(lambda: runner.train_step(net, sb, opt, cw, rate), 30)
+        gs = runner.GraphedTrainStep(net, sb, opt, cw, rate, warmup=2)
+        graph_ms, graph_wall = timed(gs, 100)
+        gs.reset_salt()
+        one = synth_device.make_batch(first_tree=7, count=1, seed=SEED, ragged=True).graph
+        if pe_dim:
+            spe.distance_pos_enc(one, pos_enc_dim=pe_dim)
+        net.eval()
+        inf_ms, inf_wall = timed(lambda: runner.infer(net, one), 30)
+        net.train()
+        small = {"trees": 64, "nodes": sb.num_nodes, "train_step_eager_ms": eager_ms, "train_step_cuda_graph_ms": graph_ms,
+                 "train_graphs_per_s_cuda_graph": 64 / (graph_ms / 1e3), "train_graphs_per_s_eager": 64 / (eager_ms / 1e3),
+                 "single_scan_inference_ms": inf_wall, "single_scan_inference_gpu_ms": inf_ms,
+                 "what": "64 ragged trees per step (the reference's TRAIN_BATCH_SIZE); CUDA-graph replay of the whole "
+                         "train step with per-replay dropout/sampling masks; inference latency of ONE scan (graph → "
+                         "logits → per-class arg-max), host wall clock"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:     # reported at N=1 only (at N>1 the ranks share the host cores)
         cores = os.cpu_count() or 1
@@ -431,7 +469,7 @@ def run_ours(args):
                        "loss": loss_val},
             "roofline": roof, "roofline_agg": roof_agg, "kernel_time_shares": shares, "abi_ms_per_step": abi_ms,
             "cpu_baseline": cpu, "e2e": e2e, "e2e_dense_format": e2e_dense, "h2d_only": h2d_only,
-            "stream_1M_trees": stream_line, "gpu_launches": int(launches),
+            "stream_1M_trees": stream_line, "small_batch": small, "gpu_launches": int(launches),
             "gpu_launches_per_step": int(launches) // args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
@@ -456,6 +494,7 @@ def main():
     ap.add_argument("--stream-steps", type=int, default=10, help="extra steps on freshly generated batches (config 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the 64-tree / single-scan latency leg")
     ap.add_argument("--gemm-mode", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -412,6 +412,13 @@ int spgnn_masked_ce_bwd(const float* logits, int64_t ld, int64_t n_class, const 
 /* SGD with momentum over a flat bucket (torch.optim.SGD semantics: buf = mu*buf + g; p -= lr*buf). */
 int spgnn_sgd_momentum(float* p, const float* g, float* buf, int64_t n, float lr, float mu, float grad_scale,
                        int first_step, void* stream);
+/* Per-step salt of every dropout / sampling seed (seeds are kernel arguments: a step replayed from a CUDA graph would
+ * repeat its masks).  Copies *dev_value (device memory, e.g. a step counter bumped by the first node of the captured
+ * step) into the library's constant-memory salt, stream-ordered and capturable; every mask of the kernels that
+ * follow uses seed + salt * 0x9E3779B97F4A7C15.  The salt is 0 until this is called.  spgnn_seed_salt_units: number
+ * of translation units holding a copy (one memcpy node each). */
+int spgnn_seed_salt_set(const uint64_t* dev_value, void* stream);
+int spgnn_seed_salt_units(void);
 /* The full update of torch.optim.SGD (the reference's optimiser, job_runner.py:239-249 with
  * exp_settings OPTIMIZER = {momentum, lr[, weight_decay, dampening, nesterov]}) over a contiguous range of the bucket:
  *   g = grad_scale*g + weight_decay*p;  buf = first_step ? g : mu*buf + (1-dampening)*g  (mu != 0);

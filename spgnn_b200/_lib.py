@@ -60,7 +60,7 @@ class _Lib:
             fn.restype = restype
             fn.argtypes = argtypes
         self._status = {n for n, r, _ in self.protos if r is ctypes.c_int and n not in
-                        ("spgnn_abi_version",)}
+                        ("spgnn_abi_version", "spgnn_seed_salt_units")}
         self.profile = None          # when a list: (name, key, start_event, stop_event) per C-ABI call
 
     def last_error(self):

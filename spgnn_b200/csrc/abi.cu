@@ -25,6 +25,11 @@ int sm_count() {
     }
     return cached;
 }
+static SaltSetter g_salt_setters[32];
+static int g_n_salt_setters = 0;
+SaltRegistrar::SaltRegistrar(SaltSetter fn) {
+    if (g_n_salt_setters < 32) g_salt_setters[g_n_salt_setters++] = fn;
+}
 static unsigned long long device_bit() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return 0ull;      // unknown device: never cached
@@ -37,6 +42,21 @@ void DeviceOnce::done() { __atomic_fetch_or(&mask, device_bit(), __ATOMIC_RELEAS
 extern "C" const char* spgnn_last_error(void) { return spgnn::g_err; }
 extern "C" int spgnn_abi_version(void) { return 1; }
 extern "C" int64_t spgnn_launch_count(void) { return (int64_t)spgnn::launches(); }
+__global__ void salt_zero_kernel(unsigned long long* p) { *p = 0ull; }
+
+extern "C" int spgnn_seed_salt_set(const uint64_t* dev_value, void* stream) {
+    SPGNN_REQUIRE(dev_value, "seed_salt_set: null pointer");
+    for (int i = 0; i < spgnn::g_n_salt_setters; ++i) {
+        const int e = spgnn::g_salt_setters[i](dev_value, spgnn::as_stream(stream));
+        if (e != 0) {
+            spgnn::set_error("seed_salt_set: cudaMemcpyToSymbolAsync failed: %s", cudaGetErrorString((cudaError_t)e));
+            return SPGNN_E_CUDA;
+        }
+    }
+    return SPGNN_OK;
+}
+extern "C" int spgnn_seed_salt_units(void) { return spgnn::g_n_salt_setters; }
+
 extern "C" int spgnn_device_info(int* sm, int* major, int* minor) {
     int dev = 0;
     SPGNN_CUDA_OK(cudaGetDevice(&dev));

@@ -357,3 +357,5 @@ extern "C" int spgnn_concat_dropout_bwd(const float* g, int64_t ldg, int64_t K1,
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(aggs)

@@ -101,6 +101,28 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope
     }
 }
 
+// Per-step salt of every dropout / sampling seed.  Seeds are kernel ARGUMENTS (host-side counters): a training step
+// replayed from a CUDA graph would draw the same masks every time.  The salt lives in constant memory (one copy per
+// translation unit, read through the constant cache at no cost), is 0 in eager execution and is refreshed by the
+// first nodes of a captured step from a device-side counter (spgnn_seed_salt_set: one D2D cudaMemcpyToSymbolAsync
+// per translation unit, itself captured), so replay k uses seed + k * golden-ratio for every mask of the step.
+static __constant__ unsigned long long g_seed_salt = 0ull;
+typedef int (*SaltSetter)(const void* dev_src, cudaStream_t st);
+struct SaltRegistrar { explicit SaltRegistrar(SaltSetter fn); };
+#define SPGNN_REGISTER_SALT(tag)                                                                              \
+    static int set_seed_salt_##tag(const void* dev_src, cudaStream_t st) {                                   \
+        return (int)cudaMemcpyToSymbolAsync(spgnn::g_seed_salt, dev_src, sizeof(unsigned long long), 0,      \
+                                            cudaMemcpyDeviceToDevice, st);                                   \
+    }                                                                                                         \
+    static spgnn::SaltRegistrar salt_registrar_##tag(set_seed_salt_##tag);
+__host__ __device__ __forceinline__ uint64_t salted(uint64_t seed) {
+#ifdef __CUDA_ARCH__
+    return seed + g_seed_salt * 0x9E3779B97F4A7C15ull;
+#else
+    return seed;
+#endif
+}
+
 // Counter-based hash -> uniform in [0,1): two rounds of a 64-bit finaliser (splitmix64).  Used for
 // dropout / node-sampling masks so that backward can regenerate the forward mask from (seed, index).
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -118,13 +140,14 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     return h ^ (h >> 16);
 }
 __host__ __device__ __forceinline__ uint64_t chunk_hash(uint64_t seed, uint64_t idx) {
+    seed = salted(seed);
     const uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
     const uint32_t a = fmix32(((uint32_t)seed ^ (lo * 0x9E3779B1u)) + hi * 0x85EBCA77u);
     const uint32_t b = fmix32(((uint32_t)(seed >> 32) ^ (lo * 0xC2B2AE3Du) ^ a) + hi * 0x27D4EB2Fu);
     return (uint64_t)a | ((uint64_t)b << 32);
 }
 __host__ __device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
-    uint64_t h = mix64(seed ^ mix64(idx));
+    uint64_t h = mix64(salted(seed) ^ mix64(idx));
     return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);   // 24 random bits
 }
 

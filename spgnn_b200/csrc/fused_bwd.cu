@@ -127,3 +127,5 @@ extern "C" int spgnn_act_bwd_planes(const float* g, int64_t ldg, const float* y,
     }
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(fused_bwd)

@@ -629,3 +629,5 @@ extern "C" int spgnn_gat_agg_bwd(const float* g_out, int64_t ldg, const float* o
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(gat)

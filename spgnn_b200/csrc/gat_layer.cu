@@ -509,3 +509,5 @@ extern "C" int spgnn_gat_layer_bwd(const spgnn_gat_layer* L, void* stream) {
     }
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(gat_layer)

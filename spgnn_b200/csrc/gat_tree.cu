@@ -270,7 +270,25 @@ static size_t bwd_smem_bytes(int nmax, int H, int HF, int nstages) {
            (size_t)(nstages + 1) * nmax * kCS * 4 + 128;
 }
 
-template <int NG>
+// d act(x) / dx from the pre-activation, for the activation known at compile time (ACT = SPGNN_ACT_ELU / _TANH: one
+// exponential and no compare chain on the runtime code; anything else takes the generic pair act / act-grad-from-output)
+template <int ACT>
+__device__ __forceinline__ float act_slope(float x, int act) {
+    if (ACT == SPGNN_ACT_ELU) return x > 0.f ? 1.f : exp_fast(x);
+    if (ACT == SPGNN_ACT_TANH) {
+        const float y = 1.f - __fdividef(2.f, exp_fast(2.f * x) + 1.f);
+        return 1.f - y * y;
+    }
+    return act_grad_from_out(act_fast(x, act), act, 0.f);
+}
+template <int ACT>
+__device__ __forceinline__ float4 act_slope4(float4 p, int act) {
+    return make_float4(act_slope<ACT>(p.x, act), act_slope<ACT>(p.y, act), act_slope<ACT>(p.z, act), act_slope<ACT>(p.w, act));
+}
+
+// NG gradient sources; ACT: activation known at compile time (0 = read it from the arguments); KPER: rounds of 64
+// nodes a slice takes (5 covers trees of up to 320 nodes and frees 4 * (1 + NG) prefetch registers)
+template <int NG, int ACT, int KPER>
 __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_constant__ CUtensorMap zmap, const TArgs t) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Args& a = t.a;
@@ -303,12 +321,12 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
         }
     }
     // own-row operands of the item about to be computed: residual projection and the raw gradient sources
-    float4 r[kPer], g[NG][kPer];
+    float4 r[KPER], g[NG][KPER];
     float4 bv = zero4();
     auto load_own = [&](const Cursor& it) {
         if (a.bias) bv = ldg4(a.bias + it.s * kCS + l8 * 4);
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
+        for (int k = 0; k < KPER; ++k) {
             const int i = qw + k * kQW;
             const bool on = i < it.n;
             const int64_t v = it.n0 + i;
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
         const int h = (s * kCS) / F;
         float4 bsum = zero4();
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
+        for (int k = 0; k < KPER; ++k) {
             const int i = qw + k * kQW;
             if (i < n) {
                 const int64_t v = n0 + i;
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
                     go = add4(go, drop4(g[q][k], gq_.thr, gq_.scale, gq_.seed,
                                         (uint64_t)v * (uint64_t)gq_.nch + (uint64_t)(gq_.ch_off + (c >> 2))));
                 }
-                const float4 gq = mul4(go, actgrad4(act4(acc, a.act), a.act));
+                const float4 gq = mul4(go, act_slope4<ACT>(acc, a.act));
                 sts4(gsm + i * (kCS * 4), gq);
                 if (has_res) store_planes4(a.dY + v * a.dld + a.res_off + c, a.dps, gq);
                 bsum = add4(bsum, gq);
@@ -440,28 +458,36 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
         // (the per-round chain list -> gather -> FMA -> store left the 4 warps of a scheduler waiting on shared-memory
         // latency: 18 % of this kernel's stall samples sat on these lines, profiles/r01_ncu_tree_bwd_source.txt).
 #pragma unroll
-        for (int k0 = 0; k0 < kPer; k0 += kBatch) {
+        for (int k0 = 0; k0 < KPER; k0 += kBatch) {
+            constexpr int kB = kBatch;
+            const int nb_ = KPER - k0 < kB ? KPER - k0 : kB;   // rounds in this batch (compile-time after unrolling)
             if ((qw & ~3) + k0 * kQW < n) {                    // warp-uniform: this warp has a node in round k0
-                short4s nb[kBatch];
-                float4 w[kBatch], acc[kBatch];
+                short4s nb[kB];
+                float4 w[kB], acc[kB];
 #pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    const int i = qw + (k0 + j) * kQW;
-                    const int ii = i < n ? i : 0;
-                    nb[j] = st.onb[ii];
-                    w[j] = *reinterpret_cast<const float4*>(st.ow + (ii * H + h) * 4);
+                for (int j = 0; j < kB; ++j) {
+                    if (j < nb_) {
+                        const int i = qw + (k0 + j) * kQW;
+                        const int ii = i < n ? i : 0;
+                        nb[j] = st.onb[ii];
+                        w[j] = *reinterpret_cast<const float4*>(st.ow + (ii * H + h) * 4);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    acc[j] = scale4(w[j].x, lds4(gsm + nb[j].x * (kCS * 4)));
-                    acc[j] = fma4(w[j].y, lds4(gsm + nb[j].y * (kCS * 4)), acc[j]);
-                    acc[j] = fma4(w[j].z, lds4(gsm + nb[j].z * (kCS * 4)), acc[j]);
-                    acc[j] = fma4(w[j].w, lds4(gsm + nb[j].w * (kCS * 4)), acc[j]);
+                for (int j = 0; j < kB; ++j) {
+                    if (j < nb_) {
+                        acc[j] = scale4(w[j].x, lds4(gsm + nb[j].x * (kCS * 4)));
+                        acc[j] = fma4(w[j].y, lds4(gsm + nb[j].y * (kCS * 4)), acc[j]);
+                        acc[j] = fma4(w[j].z, lds4(gsm + nb[j].z * (kCS * 4)), acc[j]);
+                        acc[j] = fma4(w[j].w, lds4(gsm + nb[j].w * (kCS * 4)), acc[j]);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    const int i = qw + (k0 + j) * kQW;
-                    if (i < n) store_planes4(a.dY + (n0 + i) * a.dld + c, a.dps, acc[j]);
+                for (int j = 0; j < kB; ++j) {
+                    if (j < nb_) {
+                        const int i = qw + (k0 + j) * kQW;
+                        if (i < n) store_planes4(a.dY + (n0 + i) * a.dld + c, a.dps, acc[j]);
+                    }
                 }
             }
         }
@@ -597,15 +623,27 @@ int launch_bwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* h
     t.nstages = bwd_smem_bytes(t.nmax, a.H, HF, 2) <= kSmemLimit ? 2 : 1;
     const size_t smem = bwd_smem_bytes(t.nmax, a.H, HF, t.nstages);
     if (smem > kSmemLimit) return SPGNN_OK;
+    using BwdFn = void (*)(const CUtensorMap, const TArgs);
+    // [NG - 1][ACT: 0 generic, 1 ELU, 2 tanh][KPER - 5]
+    static const BwdFn table[2][3][2] = {
+        {{gat_tree_bwd_kernel<1, 0, 5>, gat_tree_bwd_kernel<1, 0, 6>},
+         {gat_tree_bwd_kernel<1, SPGNN_ACT_ELU, 5>, gat_tree_bwd_kernel<1, SPGNN_ACT_ELU, 6>},
+         {gat_tree_bwd_kernel<1, SPGNN_ACT_TANH, 5>, gat_tree_bwd_kernel<1, SPGNN_ACT_TANH, 6>}},
+        {{gat_tree_bwd_kernel<2, 0, 5>, gat_tree_bwd_kernel<2, 0, 6>},
+         {gat_tree_bwd_kernel<2, SPGNN_ACT_ELU, 5>, gat_tree_bwd_kernel<2, SPGNN_ACT_ELU, 6>},
+         {gat_tree_bwd_kernel<2, SPGNN_ACT_TANH, 5>, gat_tree_bwd_kernel<2, SPGNN_ACT_TANH, 6>}}};
     static DeviceOnce attr;
     if (attr.pending()) {
-        SPGNN_CUDA_OK(cudaFuncSetAttribute(gat_tree_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        SPGNN_CUDA_OK(cudaFuncSetAttribute(gat_tree_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        for (auto& per_ng : table)
+            for (auto& per_act : per_ng)
+                for (BwdFn fn : per_act)
+                    SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         attr.done();
     }
     const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
-    if (a.n_g == 1) gat_tree_bwd_kernel<1><<<grid, kThreads, smem, st>>>(zmap, t);
-    else gat_tree_bwd_kernel<2><<<grid, kThreads, smem, st>>>(zmap, t);
+    const int act_i = a.act == SPGNN_ACT_ELU ? 1 : (a.act == SPGNN_ACT_TANH ? 2 : 0);
+    const int kper_i = L->max_nodes <= 5 * kQW ? 0 : 1;
+    table[a.n_g - 1][act_i][kper_i]<<<grid, kThreads, smem, st>>>(zmap, t);
     SPGNN_LAUNCH_OK();
     if (L->dbias) {
         tree_dbias_reduce_kernel<<<(unsigned)ceil_div(HF, 128), 128, 0, st>>>(a.dbias_ws, grid, HF, L->dbias);
@@ -617,3 +655,5 @@ int launch_bwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* h
 
 }  // namespace tree
 }  // namespace spgnn
+
+SPGNN_REGISTER_SALT(gat_tree)

@@ -476,3 +476,5 @@ extern "C" int spgnn_gat_aggx_bwd(const spgnn_gat_wide* L, void* stream) {
     WIDE_DISPATCH(aggx_bwd_src_kernel, a);
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(gat_wide)

@@ -1295,3 +1295,5 @@ extern "C" int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, 
     reduce_splits(a.out, t.splits * a.chunks_per_split, N, Kt, dW, lddw, st);
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(gemm_tma)

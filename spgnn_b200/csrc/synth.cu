@@ -192,3 +192,5 @@ extern "C" int spgnn_synth_features(int64_t first_tree, int64_t B, uint32_t seed
     }
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(synth)

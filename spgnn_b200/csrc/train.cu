@@ -145,3 +145,5 @@ extern "C" int spgnn_sgd_momentum(float* p, const float* g, float* buf, int64_t 
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }
+
+SPGNN_REGISTER_SALT(train)

@@ -219,13 +219,25 @@ class GCNTrain(_Runner):
         self.model.train()
         g = self.to_device(scans)
         losses = []
-        for n in range(s.GCN_STEPS if steps is None else steps):
-            loss = runner.train_step(self.model, g, self.optimizer, self.class_w, s.SAMPLING_RATE)
+        n_steps = s.GCN_STEPS if steps is None else steps
+        # many steps on one batch: capture the step once and replay it (launch-bound at the reference's batch size)
+        graphed = None
+        if getattr(s, "USE_CUDA_GRAPH", True) and n_steps >= 16 and self.optimizer.world == 1:
+            graphed = runner.GraphedTrainStep(self.model, g, self.optimizer, self.class_w, s.SAMPLING_RATE, warmup=3)
+            first = 3                                      # the warm-up steps are real training steps
+        else:
+            first = 0
+        self.current_iteration += first
+        for n in range(first, n_steps):
+            loss = graphed() if graphed is not None else \
+                runner.train_step(self.model, g, self.optimizer, self.class_w, s.SAMPLING_RATE)
             if n % s.LOG_STEPS == 0:
                 losses.append(float(loss.item()))
                 self.logger.info("Step %d-%d, LOSS: %.5f, LR:%.5f.", self.epoch_n, self.current_iteration, losses[-1],
                                  self.optimizer.lr)
             self.current_iteration += 1
+        if graphed is not None:
+            graphed.reset_salt()
         return losses
 
     @torch.no_grad()

@@ -158,7 +158,55 @@ def train_step(net, g, opt, class_w, sampling_rate, mask=None, group=None):
                                     reduce_fn=_allreduce_sums(group))
     loss.backward()
     opt.step()
-    return loss
+    # detached: a caller that keeps the loss must not keep the step's autograd graph (and the parameters'
+    # AccumulateGrad nodes, bound to the stream they were created on) alive into the next step / a graph capture
+    return loss.detach()
+
+
+class GraphedTrainStep:
+    """The GCN_STEPS loop of the reference (job_runner.py:1892-1919: 300 steps on ONE batch) as a CUDA graph.
+
+    At the reference's own batch size (64 scans, ~19 k nodes) a step is ~115 kernel launches of a few microseconds
+    each: the GPU waits for the host.  The step is captured once per batch and replayed: the learning rate, the
+    momentum-buffer state and every pointer are frozen in the graph, the dropout / sampling masks are NOT — the first
+    nodes of the graph bump a device-side step counter and copy it into the library's seed salt
+    (``spgnn_seed_salt_set``), so replay k draws the masks of seed + k.  ``loss`` is a device tensor refreshed by every
+    replay.  Re-capture (a new object) when the batch or the learning rate changes; world_size > 1 stays eager."""
+
+    def __init__(self, net, g, opt, class_w, sampling_rate, warmup=3, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            raise RuntimeError("GraphedTrainStep: data-parallel steps are not captured (use train_step)")
+        self.net, self.g, self.opt = net, g, opt
+        dev = class_w.device
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        g.max_degree()                                  # the builder's flags: read once, before the capture
+        g.check_no_zero_in_degree()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):        # eager: allocator pools, momentum buffers, lazy attributes
+                train_step(net, g, opt, class_w, sampling_rate)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.lr = opt.lr
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.counter.add_(1)
+            lib().seed_salt_set(ptr(self.counter), stream())
+            self.loss = train_step(net, g, opt, class_w, sampling_rate)
+        self.replays = 0
+
+    def __call__(self):
+        if self.opt.lr != self.lr:
+            raise RuntimeError("GraphedTrainStep: the learning rate changed since the capture; build a new one")
+        self.graph.replay()
+        self.replays += 1
+        self.opt.steps += 1
+        return self.loss
+
+    def reset_salt(self):
+        """Back to eager semantics for whatever runs next on this device (salt 0)."""
+        self.counter.zero_()
+        lib().seed_salt_set(ptr(self.counter), stream())
 
 
 @torch.no_grad()

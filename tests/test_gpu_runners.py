@@ -168,3 +168,65 @@ def test_packed_wire_format_decodes_to_the_dense_batch_bit_for_bit():
     a = next(iter(runner.DeviceBatchLoader([job_runner.host_batch(big, packed=True)], pos_enc_dim=39)))
     b = next(iter(runner.DeviceBatchLoader([job_runner.host_batch(big, packed=False)], pos_enc_dim=39)))
     assert torch.equal(a.ndata["pos_enc"], b.ndata["pos_enc"]) and torch.equal(a.ndata["fvs"], b.ndata["fvs"])
+
+
+def test_seed_salt_changes_every_mask_and_resets():
+    """spgnn_seed_salt_set: the same (p, seed) draws a different dropout mask under a different salt (what lets a
+    CUDA-graph replay of a step draw fresh masks although its seeds are frozen kernel arguments), salt 0 restores it."""
+    from spgnn_b200 import ops
+    from spgnn_b200._lib import lib, ptr, stream
+    assert lib()._dll.spgnn_seed_salt_units() >= 8
+    salt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    base = ops.drop_mask(500, 64, 0.3, 1234, "cuda")
+    try:
+        salt.fill_(5)
+        lib().seed_salt_set(ptr(salt), stream())
+        other = ops.drop_mask(500, 64, 0.3, 1234, "cuda")
+        assert not torch.equal(base, other) and abs(float((other > 0).float().mean()) - 0.7) < 0.02
+        again = ops.drop_mask(500, 64, 0.3, 1234, "cuda")
+        assert torch.equal(other, again)
+    finally:
+        salt.zero_()
+        lib().seed_salt_set(ptr(salt), stream())
+    assert torch.equal(ops.drop_mask(500, 64, 0.3, 1234, "cuda"), base)
+
+
+def test_cuda_graph_step_matches_eager_and_redraws_masks():
+    """runner.GraphedTrainStep on a 6-tree batch: (a) without any randomness (dropout 0, every node kept) the replayed
+    steps reproduce the eager steps; (b) with dropout two objects built from the same state replay the same sequence
+    (deterministic; that the salt redraws every mask is test_seed_salt_changes_every_mask_and_resets)."""
+    from spgnn_b200 import models as sm, ops, pe as spe, runner, synth_device
+    from helpers import FULL_MODELS, rel_err
+    kind, cfg = FULL_MODELS["st_pgat_spgnn_3"]
+    g = synth_device.make_batch(0, 6, ragged=True).graph
+    spe.distance_pos_enc(g, pos_enc_dim=39)
+    cw = torch.tensor(runner.CLASS_WEIGHTS_22, device="cuda")
+
+    def fresh(drop):
+        torch.manual_seed(0)
+        net = sm.GATPositionSPGNNNet(**dict(cfg, feat_drop=drop, attn_drop=drop)).cuda()
+        net.init()
+        net.train()
+        net.set_gcn_only()
+        ops.manual_seed(3)
+        return net, runner.FlatSGD(net.parameters(), lr=5e-3, momentum=0.9)
+
+    # (a) no randomness: eager 3 warm-up + 4 steps == graphed (3 warm-up inside) + 4 replays
+    net_e, opt_e = fresh(0.0)
+    eager = [float(runner.train_step(net_e, g, opt_e, cw, 1.0).item()) for _ in range(7)]
+    net_g, opt_g = fresh(0.0)
+    gs = runner.GraphedTrainStep(net_g, g, opt_g, cw, 1.0, warmup=3)
+    replayed = [float(gs().item()) for _ in range(4)]
+    gs.reset_salt()
+    assert np.allclose(replayed, eager[3:], rtol=2e-4), (replayed, eager)         # replay k is training step 3 + k
+    assert rel_err(opt_g.flat_p.cpu(), opt_e.flat_p.cpu()) < 1e-4
+    # (b) with dropout: deterministic, and masks are redrawn per replay
+    seqs = []
+    for _ in range(2):
+        net_d, opt_d = fresh(0.3)
+        gd = runner.GraphedTrainStep(net_d, g, opt_d, cw, 0.15, warmup=2)
+        seqs.append([float(gd().item()) for _ in range(6)])
+        gd.reset_salt()
+    # same masks on both runs (only the atomics of the bias-gradient sums reorder)
+    assert np.allclose(seqs[0], seqs[1], rtol=1e-5) and np.isfinite(seqs[0]).all()
+    assert int(gd.counter.item()) == 0 and gd.replays == 6
