@@ -15,7 +15,7 @@ for r in rows[1:]:
     u = r[iU]
     ms = v / 1e6 if u in ("ns", "nsecond") else v / 1e3 if u in ("us", "usecond") else v if u in ("ms", "msecond") else v * 1e3
     L.append((r[iK].split("(")[0][-70:], ms, r[iG], r[iB]))
-marker = sys.argv[2] if len(sys.argv) > 2 else "sgd_momentum"
+marker = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "sgd_"
 ends = [i for i, x in enumerate(L) if marker in x[0]]
 if len(ends) >= 2:
     # a training step = the launches between two optimiser updates; bench.py also runs inference passes between its

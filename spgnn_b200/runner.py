@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import graph as sg, ops, pe as spe
+from . import dist as sdist, graph as sg, ops, pe as spe
 from ._lib import lib, ptr, stream
 
 CLASS_WEIGHTS_22 = [0.2] + [0.8] * 21      # exp_settings/st_pgat_spgnn_3.py:70-74 via job_runner.py:1867
@@ -97,8 +97,7 @@ class FlatSGD:
 
     def step(self):
         live = self._gather()
-        if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        sdist.allreduce_sum_(self.flat_g, self.group)      # the ONE gradient collective of a step (no-op at world 1)
         esz = 4
         for o, k, first in self._runs(live):
             lib().sgd_step(self.flat_p.data_ptr() + o * esz, self.flat_g.data_ptr() + o * esz,
@@ -144,8 +143,7 @@ def _allreduce_sums(group=None):
         return None
 
     def fn(sums):
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        return sums
+        return sdist.allreduce_sum_(sums, group)       # (Σ w·nll, Σ w) over all ranks: the loss is the GLOBAL mean
     return fn
 
 
