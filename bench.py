@@ -71,9 +71,22 @@ def ncu_traffic(op, trees):
         return None
     d = json.load(open(p))
     k = d.get("kernels", {}).get(NCU_KERNEL.get(op, ""))
-    if not k or d.get("trees") != trees:
-        return None
+    if not k or d.get("trees") != trees or d.get("csrc_sha16") != csrc_sha16():
+        return None                     # no capture at this size, or captured from other kernel sources: stale
     return k["dram_bytes_per_launch"]
+
+
+def csrc_sha16():
+    """sha256 (first 16 hex) over the CUDA sources: profiles/ncu_traffic.json carries the value of the build it was
+    captured from (scripts/ncu_traffic.py) and is ignored when the kernels have changed since."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "spgnn_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def peaks():
@@ -163,6 +176,52 @@ def cpu_oracle_rate(trees, steps, warmup, threads, name=HEADLINE):
     return trees / dt, dt, int(bg.num_nodes)
 
 
+def cpu_config0_and_pe(threads):
+    """BASELINE.json configs[0] as stated — st_gat_3 INFERENCE on the CPU over 64 synthetic trees, one graph at a time
+    as GCNTest.run does (job_runner.py:840-911: graph → logits → softmax → per-class arg-max) — and BASELINE.md C3:
+    the reference's host-side positional encoding of one tree (job_runner.py:1759-1777: networkx all-pairs shortest
+    paths + diameter + the distal-leaf search, literal networkx calls), which dominates its wall clock."""
+    import numpy as np
+    import torch
+    from oracle import dgl_ops, models as om, pe as ope
+    from spgnn_b200 import synth
+    torch.set_num_threads(threads)
+    model, kind, _, _ = workload("st_gat_3")
+    scans = synth.make_scans(0, 64, seed=SEED, ragged=True)
+    torch.manual_seed(0)
+    net = om.GNNNet(kind, model)
+    net.init_like_reference()
+    net.eval()
+    graphs = []
+    for s in scans:
+        g = dgl_ops.graph_from_adj(s.adj)
+        g.ndata["fvs"] = torch.from_numpy(s.fvs)
+        graphs.append(g)
+    with torch.no_grad():
+        net(graphs[0])
+        t0 = time.perf_counter()
+        for g in graphs:
+            om.decide_per_tree(net(g)[0], g.batch_num_nodes())
+        dt = time.perf_counter() - t0
+    out = {"gat3_eval_graphs_per_s": len(graphs) / dt, "gat3_eval_ms_per_graph": dt / len(graphs) * 1e3,
+           "gat3_eval_what": "st_gat_3 eval, 64 ragged synthetic trees, one graph per forward (BASELINE config 0)"}
+    try:
+        import networkx as nx
+        t0 = time.perf_counter()
+        for s in scans[:3]:
+            a = np.array(s.adj, dtype=np.int64)
+            np.fill_diagonal(a, 0)
+            G = nx.Graph(a)
+            dict(nx.all_pairs_shortest_path_length(G))
+            nx.diameter(G)
+            ope.anchors_39(s.fvs_out, s.adj, tie_rule="reference")
+        out["networkx_pe_ms_per_tree"] = (time.perf_counter() - t0) / 3 * 1e3
+    except Exception as e:                                  # networkx missing on the box: say so
+        out["networkx_pe_ms_per_tree"] = None
+        out["networkx_pe_error"] = repr(e)
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle restatement; DGL is not installable) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -171,6 +230,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     trees = args.cpu_trees
     rate, dt, nodes = cpu_oracle_rate(trees, max(1, args.steps), max(1, min(args.warmup, 2)), cores, args.workload)
+    extra = cpu_config0_and_pe(cores) if args.workload == HEADLINE else None
     line = {
         "impl": "reference", "metric": metric_name(args.workload), "value": rate, "unit": "graphs/s",
         "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)),
@@ -181,6 +241,7 @@ def run_reference(args):
                          "sample": f"{trees} trees/step (bounded sample of the 4096-tree batch); oracle = PyTorch-CPU "
                                    f"restatement of the DGL-0.7 op sequence, torch threads = {cores}"},
         "e2e": {"value": rate, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_other_configs": extra,
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -313,11 +374,12 @@ def run_ours(args):
         prof, L.profile = L.profile, None
         agg = {}
         for name, key, a, b in prof:
-            d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0, "impl": 0.0})
             d["ms"] += a.elapsed_time(b)
             d["n"] += 1
             if key:
                 d[key[0]] += key[1]
+                d["impl"] += key[2] if len(key) > 2 else key[1]      # bytes the implementation moves by design
         total = sum(d["ms"] for d in agg.values())
         shares = {k: round(d["ms"] / total, 4) for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         abi_ms = total / n_prof          # GPU time inside this library's calls per step (the rest is launch gaps)
@@ -345,6 +407,8 @@ def run_ours(args):
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": ach / pk["hbm"], "traffic": traffic(name), "launches": d["n"],
                     "avg_ms": d["ms"] / d["n"], "algorithmic_bytes_per_launch": d["bytes"] / d["n"],
+                    "implementation_bytes_per_launch": d["impl"] / d["n"],
+                    "frac_implementation_bytes": d["impl"] / sec / 1e9 / pk["hbm"],
                     "peak_source": pk["src"] + " copy bandwidth", "share_of_step": d["ms"] / total,
                     "frac_of_nominal_8TBs": ach / 8000.0}
         dominant = max(agg.items(), key=lambda kv: kv[1]["ms"])[0]

@@ -129,3 +129,80 @@ def rw_pos_enc(adj, pos_enc_dim=39):
         mp = mp @ m
         cols.append(np.diagonal(mp).astype(np.float32))
     return np.stack(cols, axis=-1)
+
+
+# ----------------------------------------------------------------------------
+# dormant extras, literal restatements on the oracle Graph
+# ----------------------------------------------------------------------------
+def _norm_laplacian(g):
+    """job_runner.py:1632-1634 / :1814-1818: L = I - N A N with A[src, dst] and N = diag(clip(in_deg, 1)^-1/2)."""
+    n = g.num_nodes
+    a = np.zeros((n, n))
+    a[g.src.numpy(), g.dst.numpy()] = 1.0
+    d = np.clip(g.in_degrees().numpy(), 1, None) ** -0.5
+    return np.eye(n) - d[:, None] * a * d[None, :]
+
+
+def eigen_basis(g, pos_enc_dim=39):
+    """job_runner.py:1630-1645 compute_eigen_basis for ONE graph: (eigenvalues ascending, eigvec[:, 1:dim+1] fp32,
+    zero-padded to pos_enc_dim columns when n <= pos_enc_dim)."""
+    val, vec = np.linalg.eig(_norm_laplacian(g))
+    idx = val.argsort()
+    val, vec = np.real(val[idx]), np.real(vec[:, idx])
+    out = vec[:, 1:pos_enc_dim + 1].astype(np.float32)
+    if out.shape[1] < pos_enc_dim:
+        out = np.pad(out, ((0, 0), (0, pos_enc_dim - out.shape[1])))
+    return val, out
+
+
+def laplacian_pos_loss(graphs, ps, lamb, pos_enc_dim):
+    """job_runner.py:1803-1825 over a list of (unbatched) oracle graphs and their [n, k] position embeddings."""
+    import torch
+    total = []
+    for g, p in zip(graphs, ps):
+        pz = p - torch.mean(p, dim=0, keepdim=True).detach()
+        pn = pz / (torch.std(p, dim=0, keepdim=True) + 1e-7).detach()
+        n = g.num_nodes
+        L = torch.tensor(_norm_laplacian(g), dtype=p.dtype)
+        pT = torch.transpose(pn, 1, 0)
+        loss1 = torch.trace(torch.mm(torch.mm(pT, L), pn))
+        ptp = torch.mm(pT, pn) - torch.eye(pn.shape[1], dtype=p.dtype)
+        total.append((loss1 + lamb * torch.norm(ptp, p="fro")) / (pos_enc_dim * n))
+    return torch.stack(total).mean()
+
+
+class DistPosLoss:
+    """job_runner.py:1827-1861 dist_pos_loss with its ``cached_mean_pos_enc`` state; ``batch_stats`` replaces the
+    reference's ``torch.rand`` initial fill so that two implementations can be compared."""
+
+    def __init__(self, nr_class=22, pos_enc_dim=39):
+        self.nr_class, self.pos_enc_dim, self.cached_mean_pos_enc = nr_class, pos_enc_dim, None
+
+    def __call__(self, ps, ys, all_pos_encs_cache, batch_stats):
+        import torch
+        import torch.nn.functional as F
+        batch_stats = batch_stats.clone()
+        total_d, total_c = [], []
+        for b, (p, y) in enumerate(zip(ps, ys)):
+            label_mapping = {y[n].item(): n for n in range(y.shape[0]) if y[n].item() != 0}
+            existing = sorted(set(range(1, self.nr_class)) & set(label_mapping.keys()))
+            cur = []
+            for label in range(1, self.nr_class):
+                if label in label_mapping:
+                    batch_stats[b, label - 1, ::] = p[label_mapping[label]].detach()
+                    cur.append(p[label_mapping[label]])
+            cur = torch.stack(cur, dim=0)
+            if self.cached_mean_pos_enc is not None:
+                c_loss = ((cur - self.cached_mean_pos_enc[(np.asarray(existing) - 1)]) ** 2).sum()
+            else:
+                c_loss = torch.zeros(())
+            n = p.shape[0]
+            x = p.unsqueeze(0).repeat(n, 1, 1)
+            yy = p.unsqueeze(1).repeat(1, n, 1)
+            aff = torch.exp(-1.0 * torch.abs(x - yy).sum(dim=2))
+            total_d.append(F.smooth_l1_loss(aff, torch.exp(-all_pos_encs_cache[b])))
+            total_c.append(c_loss.reshape(()))
+        mean_stats = batch_stats.mean(dim=0).detach()
+        self.cached_mean_pos_enc = mean_stats if self.cached_mean_pos_enc is None \
+            else 0.15 * self.cached_mean_pos_enc + 0.85 * mean_stats
+        return torch.stack(total_d).mean(), torch.stack(total_c).mean()

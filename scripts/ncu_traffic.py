@@ -54,7 +54,11 @@ def main():
             v = val(r, key)
             if v is not None:
                 d[name] += v * (val(r, "gpu__time_duration.sum") or 0.0)      # time-weighted
-    res = {"trees": trees, "kernels": {}}
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    # stamped with the hash of the CUDA sources the capture was taken from: bench.py ignores it once they change
+    res = {"trees": trees, "csrc_sha16": bench.csrc_sha16(), "kernels": {}}
     print(f"{'kernel':34s} {'n':>3s} {'total ms':>9s} {'avg ms':>8s} {'DRAM MB/launch':>15s} {'GB/s':>7s} "
           f"{'dram%':>6s} {'l2%':>6s} {'tensor%':>8s} {'issue%':>7s}")
     for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["time_s"]):

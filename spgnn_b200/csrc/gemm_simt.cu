@@ -234,11 +234,17 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, int64_t ldx, 
         part[(int64_t)blockIdx.y * N + c] = s;
     }
 }
+// one warp per column: lane l adds the partial rows l, l + 32, ... then a butterfly (a fixed order, hence reproducible);
+// one thread per column walked 592 dependent loads: 50 us for the 22 columns of the head's bias gradient
 __global__ void colsum_final_kernel(const float* __restrict__ part, int64_t nparts, int64_t N, float* __restrict__ out) {
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < N; c += nwarps) {
         float s = 0.f;
-        for (int64_t p = 0; p < nparts; ++p) s += part[p * N + c];
-        out[c] = s;
+        for (int64_t p = lane; p < nparts; p += 32) s += part[p * N + c];
+        s = warp_sum(s);
+        if (lane == 0) out[c] = s;
     }
 }
 
@@ -350,7 +356,8 @@ extern "C" int spgnn_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, f
     dim3 grid((unsigned)ceil_div(N, 128), (unsigned)parts);
     colsum_partial_kernel<<<grid, 128, 0, st>>>(X, ldx, M, N, rpb, (float*)ws);
     SPGNN_LAUNCH_OK();
-    colsum_final_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>((const float*)ws, parts, N, out);
+    const int64_t fblocks = ceil_div(N * 32, 128), fcap = (int64_t)sm_count() * 8;
+    colsum_final_kernel<<<(unsigned)(fblocks < fcap ? fblocks : fcap), 128, 0, st>>>((const float*)ws, parts, N, out);
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }

@@ -128,10 +128,35 @@ class Graph:
         self.__dict__.update(new.__dict__)
         self.ndata = nd
 
-    def adjacency_matrix(self, transpose=False):
+    def adjacency_matrix(self, transpose=False, scipy_fmt=None):
+        """DGL 0.7 ``g.adjacency_matrix()`` (dense device tensor, A[src, dst]); with ``scipy_fmt`` ("csr" / "coo") a
+        host scipy matrix, as job_runner.py:1814 asks for."""
+        if scipy_fmt is not None:
+            return self.adjacency_matrix_scipy(transpose=transpose, fmt=scipy_fmt)
         a = torch.zeros(self.num_nodes, self.num_nodes, device=self.device)
         a[self.src, self.dst] = 1.0
         return a.t() if transpose else a
+
+    def adjacency_matrix_scipy(self, transpose=False, fmt="csr", return_edge_ids=False):
+        """``g.adjacency_matrix_scipy(return_edge_ids=False)`` (job_runner.py:1632): host scipy sparse matrix with
+        ones (or the edge ids) at [src, dst]."""
+        import scipy.sparse as sp
+        s, d = self.src.cpu().numpy(), self.dst.cpu().numpy()
+        if transpose:
+            s, d = d, s
+        vals = np.arange(self.num_edges) if return_edge_ids else np.ones(self.num_edges)
+        m = sp.coo_matrix((vals, (s, d)), shape=(self.num_nodes, self.num_nodes))
+        return m.asformat(fmt)
+
+    def to_networkx(self):
+        """``dgl.to_networkx(g)`` / ``g.to_networkx()`` (job_runner.py:1763): a host nx.MultiDiGraph with the edges in
+        id order and an ``id`` attribute per edge."""
+        import networkx as nx
+        G = nx.MultiDiGraph()
+        G.add_nodes_from(range(self.num_nodes))
+        for i, (u, v) in enumerate(zip(self.src.cpu().tolist(), self.dst.cpu().tolist())):
+            G.add_edge(u, v, id=i)
+        return G
 
     def norms(self):
         """(outdeg^-1/2, indeg^-1/2, 1/indeg, 1/outdeg), degrees clamped at 1 (GraphConv 'both', GIN 'mean')."""
@@ -217,6 +242,10 @@ def from_edges(src, dst, num_nodes, device=None):
     d = torch.as_tensor(dst, dtype=torch.int64).to(dev)
     return Graph.from_edge_lists(torch.tensor([num_nodes], dtype=torch.int64, device=dev),
                                  torch.tensor([s.numel()], dtype=torch.int64, device=dev), s, d, max_nodes=num_nodes)
+
+
+def to_networkx(g):
+    return g.to_networkx()
 
 
 def remove_self_loop(g):

@@ -343,9 +343,12 @@ def _forward(plan: StackPlan, graph, ext, packed, biases, head, training, keep):
             else:
                 sk.concat_chunks, sk.chunk_off, sk.drop_p, sk.seed = 1, 0, 0.0, 0
         hf = L.H * L.F
+        # the kernel's ALGORITHMIC bytes read z, res, el, er once and write the output ONCE; every further
+        # copy of the output (fp32 + one planes sink per distinct consumer mask) is implementation traffic
+        n_writes = len(keys) + (1 if is_out else 0)
+        algo = 4.0 * N * (hf * (2 if L.res_mode == 1 else 1) + 2 * L.H) + 4.0 * N * L.width + 4.0 * (N + 1) + 4.0 * E
         L_.gat_layer_fwd(ctypes.byref(d), stream(),
-                         _key=("bytes", 4.0 * N * (hf * (2 if L.res_mode == 1 else 1) + 2 * L.H)
-                               + 4.0 * N * L.width * (len(keys) + (1 if is_out else 0)) + 4.0 * (N + 1) + 4.0 * E))
+                         _key=("bytes", algo, algo + 4.0 * N * L.width * max(n_writes - 1, 0)))
         if is_out:
             outs[L.output] = out32
         if want_head:
@@ -570,13 +573,13 @@ def _backward(plan: StackPlan, graph, tape, packed, head, g_logits, g_outs, need
             db = torch.empty(hf, dtype=torch.float32, device=dev)
             dbw = _ws(L_.gat_layer_dbias_ws(N, L.H, L.F), dev)
         d.dbias, d.dbias_ws = ptr(db), ptr(dbw)
-        gw = sum(1 for _ in srcs) * L.width
-        L_.gat_layer_bwd(ctypes.byref(d), stream(),
-                         # reads: gradient sources, z (+ residual projection), el/er; writes: dY planes (4 bytes
-                         # per column: dz | G as the residual part | d el, d er) (+ G workspace without residual)
-                         _key=("bytes", 4.0 * N * (gw + hf * (2 if L.res_mode == 1 else 1) + 2 * L.H)
-                               + 4.0 * N * (L.ycols + (0 if L.res_mode == 1 else hf))
-                               + 8.0 * (N + 1) + 12.0 * E + 8.0 * E * L.H))
+        # algorithmic: ONE gradient of the layer output, z (+ residual projection), el/er read once; dY
+        # written once (4 bytes per column: dz | G as the residual part | d el, d er) + indices and edge scalars.
+        # Implementation: every further gradient source (one per consumer) and the G workspace without a residual.
+        algo = 4.0 * N * (L.width + hf * (2 if L.res_mode == 1 else 1) + 2 * L.H) + 4.0 * N * L.ycols \
+            + 8.0 * (N + 1) + 12.0 * E + 8.0 * E * L.H
+        impl = algo + 4.0 * N * L.width * (len(srcs) - 1) + (0.0 if L.res_mode == 1 else 4.0 * N * hf)
+        L_.gat_layer_bwd(ctypes.byref(d), stream(), _key=("bytes", algo, impl))
         d_bias[i] = db
         d_packed[i] = planes_linear_bwd_weight(dY, ins[0], ins[1] if len(ins) > 1 else None)
         # dX only over the leading inputs that are produced inside the stack

@@ -720,3 +720,65 @@ def test_flat_sgd_matches_torch_optim_sgd(mods, kw):
     if kw["momentum"]:
         for i in (0, 1, 2, 4):
             assert rel_err(sd["state"][i]["momentum_buffer"], ref_opt.state[ref_p[i]]["momentum_buffer"]) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ dormant extras
+def test_dormant_pe_extras_and_graph_api_leftovers_vs_oracle(mods):
+    """SURVEY 8f rank 4 / 8b leftovers: Laplacian-eigenvector PE (job_runner.py:1630-1645), the Laplacian and the
+    distance / compactness PE losses (:1803-1861) against their literal restatements in oracle/pe.py, and
+    ``adjacency_matrix(scipy_fmt=)`` / ``adjacency_matrix_scipy`` / ``to_networkx`` (:1814, :1632, :1763)."""
+    import scipy.sparse as sp
+    from spgnn_b200 import pe_extras
+    ope, dgl_ops, sg = mods["ope"], mods["dgl_ops"], mods["sg"]
+    rng = np.random.default_rng(4)
+    adjs = [_random_tree_adj(n, mc, rng) for n, mc in ((60, 2), (45, 3), (30, 2))]
+    g = sg.batch_from_adjs(adjs)
+    ogs = [dgl_ops.graph_from_adj(a) for a in adjs]
+    off = g.node_off.tolist()
+    # graph API
+    A = g.adjacency_matrix(scipy_fmt="csr")
+    assert sp.isspmatrix_csr(A) and A.shape == (g.num_nodes, g.num_nodes) and A.nnz == g.num_edges
+    assert np.array_equal(A.toarray(), g.adjacency_matrix().cpu().numpy())
+    ids = g.adjacency_matrix_scipy(return_edge_ids=True, fmt="coo")
+    assert np.array_equal(np.sort(ids.data), np.arange(g.num_edges))
+    G = g.to_networkx()
+    assert G.number_of_nodes() == g.num_nodes and G.number_of_edges() == g.num_edges
+    assert [(u, v) for u, v, _ in sorted(G.edges(data="id"), key=lambda e: e[2])] == \
+        list(zip(g.src.cpu().tolist(), g.dst.cpu().tolist()))
+    # eigenvector PE: eigen-pairs of the same Laplacian, same ordering (vectors agree up to sign where non-degenerate)
+    ev = pe_extras.compute_eigen_basis(g, 39).cpu().numpy()
+    assert ev.shape == (g.num_nodes, 39) and np.array_equal(g.ndata["eigvec"].cpu().numpy(), ev)
+    for i, og in enumerate(ogs):
+        val, ref = ope.eigen_basis(og, 39)
+        L = ope._norm_laplacian(og)
+        blk = ev[off[i]:off[i + 1]].astype(np.float64)
+        k = min(39, og.num_nodes - 1)
+        lam = np.einsum("nk,nk->k", blk[:, :k], L @ blk[:, :k])
+        assert np.allclose(lam, val[1:1 + k], atol=1e-5) and np.allclose(L @ blk[:, :k], blk[:, :k] * lam, atol=1e-4)
+        assert np.all(blk[:, k:] == 0)
+        gaps = np.minimum(np.abs(np.diff(val[:k + 2]))[:-1], np.abs(np.diff(val[:k + 2]))[1:])
+        for j in np.nonzero(gaps > 1e-3)[0]:
+            assert abs(abs(float(blk[:, j] @ ref[:, j].astype(np.float64))) - 1.0) < 1e-3, (i, j)
+    # losses
+    gen = torch.Generator().manual_seed(0)
+    p = torch.randn(g.num_nodes, 39, generator=gen)
+    y = torch.zeros(g.num_nodes, dtype=torch.int64)
+    for i in range(len(adjs)):
+        nodes = torch.randperm(off[i + 1] - off[i], generator=gen)[:21] + off[i]
+        y[nodes] = torch.arange(1, 22)
+    y[off[1] + 3] = 0                                         # one label missing in the second tree
+    ps = [p[off[i]:off[i + 1]] for i in range(len(adjs))]
+    ys = [y[off[i]:off[i + 1]] for i in range(len(adjs))]
+    ref = ope.laplacian_pos_loss(ogs, ps, 0.1, 39)
+    got = pe_extras.laplacian_pos_loss(g, p.cuda(), 0.1, 39)
+    assert abs(float(got) - float(ref)) < 1e-5 * abs(float(ref))
+    cache = [torch.from_numpy(ope.dist_pos_enc(a, list(range(21)))[1]) for a in adjs]
+    stats0 = torch.rand(len(adjs), 21, 39, generator=gen)
+    dev_loss, ref_loss = pe_extras.DistPosLoss(22, 39), ope.DistPosLoss(22, 39)
+    for it in range(2):                                        # second call exercises the cached running mean
+        pd = (p * (1 + 0.1 * it)).cuda().requires_grad_()
+        d1, c1 = dev_loss(g, cache, p=pd, y=y.cuda(), batch_stats_init=stats0)
+        d0, c0 = ref_loss([t * (1 + 0.1 * it) for t in ps], ys, cache, stats0)
+        assert abs(float(d1) - float(d0)) < 1e-5 * abs(float(d0)) and abs(float(c1) - float(c0)) <= 1e-4 * max(abs(float(c0)), 1e-6)
+        (d1 + c1).backward()
+        assert torch.isfinite(pd.grad).all()
