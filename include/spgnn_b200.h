@@ -377,8 +377,10 @@ int spgnn_concat_dropout_bwd(const float* g, int64_t ldg, int64_t K1, int64_t K2
  *                   {u->v : u<v adjacent} (ties -> largest index; the anchor itself when it has no descendant).
  *                   anchors int32 [B, pos_dim] LOCAL node ids; pos_dim in {21, 39}.
  *   pe_dist_init  : job_runner.py:1759-1777 — pos_enc[n,k] = hops(n, anchor_k)/diameter on the self-loop-free
- *                   graph (all-pairs bit-parallel BFS per graph gives the diameter); diam int32 [B];
- *                   flags[0] counts disconnected graphs.
+ *                   graph; diam int32 [B]; flags[0] counts disconnected graphs.  Trees (symmetric, 2(n-1) non-self
+ *                   edges, connected: every airway graph) take a kernel that runs the pos_dim anchor waves plus
+ *                   two BFS for the diameter; any other graph takes the all-pairs bit-parallel BFS.  ws:
+ *                   spgnn_pe_dist_ws_bytes(B, max_nodes) bytes, always required.
  *   pe_rw_init    : job_runner.py:1684-1702 — diag((A D^-1)^k), k=1..pos_dim, fp64 accumulate, fp32 out.
  * All take a batched adjacency (ptr, nbr; self loops are skipped) and node_off int64 [B+1].  pe_dist_init follows
  * nx shortest paths v -> anchor, so pass the OUT-CSR (out_ptr, out_dst); the others take the in-CSC.  For the

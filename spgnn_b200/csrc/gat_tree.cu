@@ -80,6 +80,18 @@ struct Cursor {
     }
 };
 
+// activation known at compile time (ACT = SPGNN_ACT_ELU / _TANH), else the runtime code
+template <int ACT>
+__device__ __forceinline__ float4 act_apply4(float4 p, int act) {
+    if (ACT == SPGNN_ACT_ELU)
+        return make_float4(p.x > 0.f ? p.x : exp_fast(p.x) - 1.f, p.y > 0.f ? p.y : exp_fast(p.y) - 1.f,
+                           p.z > 0.f ? p.z : exp_fast(p.z) - 1.f, p.w > 0.f ? p.w : exp_fast(p.w) - 1.f);
+    if (ACT == SPGNN_ACT_TANH)
+        return make_float4(1.f - __fdividef(2.f, exp_fast(2.f * p.x) + 1.f), 1.f - __fdividef(2.f, exp_fast(2.f * p.y) + 1.f),
+                           1.f - __fdividef(2.f, exp_fast(2.f * p.z) + 1.f), 1.f - __fdividef(2.f, exp_fast(2.f * p.w) + 1.f));
+    return act4(p, act);
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 struct FSmem {
     uint64_t* full; int* deg; short4s* nb; float* w; float* zs;
@@ -98,6 +110,7 @@ static size_t fwd_smem_bytes(int nmax, int H, int nstages) {
     return 128 + (size_t)nmax * (4 + 8 + H * 16) + 128 + (size_t)nstages * nmax * kCS * 4 + 128;
 }
 
+template <int ACT, int KPER>
 __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_constant__ CUtensorMap zmap, const TArgs t) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Args& a = t.a;
@@ -126,10 +139,10 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_
         if (t.nstages == 2 && nxt.valid(t))
             issue_slice(&zmap, smem_u32(&st.full[1]), zs_u32 + stage_bytes, nxt.n0, nxt.n, nxt.s * kCS);
     }
-    float4 r[kPer];              // residual rows of the item about to be computed (prefetched one slice ahead)
+    float4 r[KPER];              // residual rows of the item about to be computed (prefetched one slice ahead)
     float4 bv = a.bias ? ldg4(a.bias + l8 * 4) : zero4();
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) {
+    for (int k = 0; k < KPER; ++k) {
         const int i = qw + k * kQW;
         r[k] = (has_res && i < cur.n) ? ldg4(a.Y + (cur.n0 + i) * a.ldy + a.res_off + l8 * 4) : zero4();
     }
@@ -172,9 +185,9 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_
             __syncthreads();
         }
         // own rows of this item are in r[]; move them out and start the loads of the next item
-        float4 rc[kPer];
+        float4 rc[KPER];
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) rc[k] = r[k];
+        for (int k = 0; k < KPER; ++k) rc[k] = r[k];
         const float4 bvc = bv;
         Cursor nn = cur;
         nn.advance(t);
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_
             const float* yrow = a.Y + (nn.n0 + qw) * a.ldy + a.res_off + nn.s * kCS + l8 * 4;
             if (a.bias) bv = ldg4(a.bias + nn.s * kCS + l8 * 4);
 #pragma unroll
-            for (int k = 0; k < kPer; ++k) {
+            for (int k = 0; k < KPER; ++k) {
                 const int i = qw + k * kQW;
                 r[k] = (has_res && i < nn.n) ? ldg4(yrow + (int64_t)(k * kQW) * a.ldy) : zero4();
             }
@@ -196,29 +209,37 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_
         const int h = (s * kCS) / F;
         // rounds kBatch at a time, out-of-range nodes clamped to node 0 (see the backward's source side)
 #pragma unroll
-        for (int k0 = 0; k0 < kPer; k0 += kBatch) {
+        for (int k0 = 0; k0 < KPER; k0 += kBatch) {
+            constexpr int kB = kBatch;
+            const int nb_ = KPER - k0 < kB ? KPER - k0 : kB;   // rounds in this batch (compile-time after unrolling)
             if ((qw & ~3) + k0 * kQW < n) {                    // warp-uniform
-                short4s nb[kBatch];
-                float4 w[kBatch], acc[kBatch];
+                short4s nb[kB];
+                float4 w[kB], acc[kB];
 #pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    const int i = qw + (k0 + j) * kQW;
-                    const int ii = i < n ? i : 0;
-                    nb[j] = st.nb[ii];
-                    w[j] = *reinterpret_cast<const float4*>(st.w + (ii * H + h) * 4);
+                for (int j = 0; j < kB; ++j) {
+                    if (j < nb_) {
+                        const int i = qw + (k0 + j) * kQW;
+                        const int ii = i < n ? i : 0;
+                        nb[j] = st.nb[ii];
+                        w[j] = *reinterpret_cast<const float4*>(st.w + (ii * H + h) * 4);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    acc[j] = add4(rc[k0 + j], bvc);
-                    acc[j] = fma4(w[j].x, lds4(zs + nb[j].x * (kCS * 4)), acc[j]);
-                    acc[j] = fma4(w[j].y, lds4(zs + nb[j].y * (kCS * 4)), acc[j]);
-                    acc[j] = fma4(w[j].z, lds4(zs + nb[j].z * (kCS * 4)), acc[j]);
-                    acc[j] = fma4(w[j].w, lds4(zs + nb[j].w * (kCS * 4)), acc[j]);
+                for (int j = 0; j < kB; ++j) {
+                    if (j < nb_) {
+                        acc[j] = add4(rc[k0 + j], bvc);
+                        acc[j] = fma4(w[j].x, lds4(zs + nb[j].x * (kCS * 4)), acc[j]);
+                        acc[j] = fma4(w[j].y, lds4(zs + nb[j].y * (kCS * 4)), acc[j]);
+                        acc[j] = fma4(w[j].z, lds4(zs + nb[j].z * (kCS * 4)), acc[j]);
+                        acc[j] = fma4(w[j].w, lds4(zs + nb[j].w * (kCS * 4)), acc[j]);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < kBatch; ++j) {
-                    const int i = qw + (k0 + j) * kQW;
-                    if (i < n) emit(a, n0 + i, c, act4(acc[j], a.act));
+                for (int j = 0; j < kB; ++j) {
+                    if (j < nb_) {
+                        const int i = qw + (k0 + j) * kQW;
+                        if (i < n) emit(a, n0 + i, c, act_apply4<ACT>(acc[j], a.act));
+                    }
                 }
             }
         }
@@ -600,13 +621,20 @@ int launch_fwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* h
     t.nstages = fwd_smem_bytes(t.nmax, a.H, 2) <= kSmemLimit ? 2 : 1;
     const size_t smem = fwd_smem_bytes(t.nmax, a.H, t.nstages);
     if (smem > kSmemLimit) return SPGNN_OK;
+    using FwdFn = void (*)(const CUtensorMap, const TArgs);
+    static const FwdFn table[3][2] = {{gat_tree_fwd_kernel<0, 5>, gat_tree_fwd_kernel<0, 6>},
+                                      {gat_tree_fwd_kernel<SPGNN_ACT_ELU, 5>, gat_tree_fwd_kernel<SPGNN_ACT_ELU, 6>},
+                                      {gat_tree_fwd_kernel<SPGNN_ACT_TANH, 5>, gat_tree_fwd_kernel<SPGNN_ACT_TANH, 6>}};
     static DeviceOnce attr;
     if (attr.pending()) {
-        SPGNN_CUDA_OK(cudaFuncSetAttribute(gat_tree_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        for (auto& per_act : table)
+            for (FwdFn fn : per_act)
+                SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         attr.done();
     }
     const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
-    gat_tree_fwd_kernel<<<grid, kThreads, smem, st>>>(zmap, t);
+    const int act_i = a.act == SPGNN_ACT_ELU ? 1 : (a.act == SPGNN_ACT_TANH ? 2 : 0);
+    table[act_i][L->max_nodes <= 5 * kQW ? 0 : 1]<<<grid, kThreads, smem, st>>>(zmap, t);
     SPGNN_LAUNCH_OK();
     *handled = true;
     return SPGNN_OK;

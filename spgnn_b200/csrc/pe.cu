@@ -103,6 +103,128 @@ __global__ void __launch_bounds__(kPeThreads) anchor_select_kernel(const float* 
     }
 }
 
+// Fast path for TREES (what airway graphs are: dataset.py:409-417): the encoding needs hop counts from the pos_dim
+// anchors only, and the diameter of a tree is the eccentricity of the node farthest from any start node (two BFS).
+// One 64-bit reach mask per node — bit k: anchor k's wave has arrived, bit pos_dim: the wave of node 0 — instead
+// of the n x n bitsets of the general kernel below: ~5x less shared-memory work and 10 KB instead of 24 KB per CTA.
+// A graph is taken here iff it is symmetric, has exactly 2 (n - 1) non-self edges and node 0 reaches every node;
+// everything else (cycles, directed or disconnected graphs) is left to the all-pairs kernel (done[g] = 0).
+__global__ void __launch_bounds__(kPeThreads) pe_dist_tree_kernel(const int64_t* __restrict__ node_off,
+                                                                  const int32_t* __restrict__ ptr,
+                                                                  const int32_t* __restrict__ nbr,
+                                                                  const int32_t* __restrict__ anchors, int pos_dim,
+                                                                  float* __restrict__ pe, int64_t ldp,
+                                                                  int32_t* __restrict__ diam, int32_t* __restrict__ done) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_flag, s_edges, s_far, s_lvl_far;
+    __shared__ int s_anchor[64];
+    const int64_t base = node_off[blockIdx.x];
+    const int n = (int)(node_off[blockIdx.x + 1] - base);
+    unsigned long long* cur = reinterpret_cast<unsigned long long*>(smem);
+    unsigned long long* nxt = cur + n;
+    int* d2 = reinterpret_cast<int*>(nxt + n);              // second BFS: hops from the far node
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    // ---- a symmetric graph with 2 (n - 1) non-self edges?
+    if (tid == 0) { s_flag = 0; s_edges = 0; s_far = 0; }
+    if (tid < pos_dim) s_anchor[tid] = anchors[(int64_t)blockIdx.x * pos_dim + tid];
+    __syncthreads();
+    int nonself = 0, asym = 0;
+    for (int v = tid; v < n; v += nt) {
+        for (int e = ptr[base + v]; e < ptr[base + v + 1]; ++e) {
+            const int u = nbr[e] - (int)base;
+            if (u == v) continue;
+            ++nonself;
+            bool back = false;
+            for (int f = ptr[base + u]; f < ptr[base + u + 1]; ++f) back |= (nbr[f] - (int)base) == v;
+            asym |= !back;
+        }
+    }
+    if (nonself) atomicAdd(&s_edges, nonself);
+    if (asym) s_flag = 1;
+    __syncthreads();
+    if (s_flag != 0 || s_edges != 2 * (n - 1)) {             // uniform: shared values after the barrier
+        if (tid == 0) done[blockIdx.x] = 0;
+        return;
+    }
+    // ---- BFS 1: waves of the anchors (bits 0..pos_dim-1) and of node 0 (bit pos_dim), level-synchronous
+    const unsigned long long root_bit = 1ull << pos_dim;
+    for (int v = tid; v < n; v += nt) {
+        unsigned long long m = v == 0 ? root_bit : 0ull;
+        for (int k = 0; k < pos_dim; ++k) m |= (s_anchor[k] == v) ? (1ull << k) : 0ull;
+        cur[v] = m;
+        for (int k = 0; k < pos_dim; ++k) pe[(base + v) * ldp + k] = ((m >> k) & 1ull) ? 0.f : -1.f;
+    }
+    __syncthreads();
+    for (int level = 1;; ++level) {
+        if (tid == 0) { s_flag = 0; s_lvl_far = -1; }
+        __syncthreads();
+        for (int v = tid; v < n; v += nt) {
+            const unsigned long long old = cur[v];
+            unsigned long long m = old;
+            for (int e = ptr[base + v]; e < ptr[base + v + 1]; ++e) m |= cur[nbr[e] - (int)base];
+            nxt[v] = m;
+            unsigned long long fresh = m & ~old;
+            if (fresh) {
+                s_flag = 1;
+                if (fresh & root_bit) {
+                    atomicMax(&s_lvl_far, v);                 // the deepest level reached from node 0 wins (below)
+                    fresh &= ~root_bit;
+                }
+                while (fresh) {
+                    const int k = __ffsll((long long)fresh) - 1;
+                    fresh &= fresh - 1;
+                    pe[(base + v) * ldp + k] = (float)level;
+                }
+            }
+        }
+        __syncthreads();
+        if (!s_flag) break;                                   // uniform
+        if (tid == 0 && s_lvl_far >= 0) s_far = s_lvl_far;
+        unsigned long long* t = cur; cur = nxt; nxt = t;
+        __syncthreads();
+    }
+    // node 0 must have reached every node (a forest plus a cycle has the edge count of a tree)
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    int unreached = 0;
+    for (int v = tid; v < n; v += nt) unreached |= !(cur[v] & root_bit);
+    if (unreached) s_flag = 1;
+    __syncthreads();
+    if (s_flag) {
+        if (tid == 0) done[blockIdx.x] = 0;
+        return;
+    }
+    // ---- BFS 2 from the node farthest from node 0: its eccentricity is the diameter of the tree
+    const int far = s_far;
+    for (int v = tid; v < n; v += nt) d2[v] = v == far ? 0 : -1;
+    __syncthreads();
+    int ecc = 0;
+    while (true) {
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        for (int v = tid; v < n; v += nt) {
+            if (d2[v] != -1) continue;
+            bool hit = false;
+            for (int e = ptr[base + v]; e < ptr[base + v + 1]; ++e) hit |= d2[nbr[e] - (int)base] == ecc;
+            if (hit) { d2[v] = -2 - ecc; s_flag = 1; }        // joins level ecc + 1 after the barrier
+        }
+        __syncthreads();
+        if (!s_flag) break;                                   // uniform
+        ++ecc;
+        for (int v = tid; v < n; v += nt)
+            if (d2[v] == -1 - ecc) d2[v] = ecc;
+        __syncthreads();
+    }
+    if (tid == 0) { diam[blockIdx.x] = ecc; done[blockIdx.x] = 1; }
+    const float fd = (float)ecc;
+    for (int i = tid; i < n * pos_dim; i += nt) {
+        const int v = i / pos_dim, k = i - v * pos_dim;
+        float* q = pe + (base + v) * ldp + k;
+        *q = ecc > 0 ? __fdiv_rn(*q, fd) : 0.f;
+    }
+}
+
 // reach[2][n][W] bitsets in shared memory (or in `ws` when too large)
 __global__ void __launch_bounds__(kPeThreads) pe_dist_kernel(const int64_t* __restrict__ node_off,
                                                              const int32_t* __restrict__ in_ptr,
@@ -110,10 +232,11 @@ __global__ void __launch_bounds__(kPeThreads) pe_dist_kernel(const int64_t* __re
                                                              const int32_t* __restrict__ anchors, int pos_dim,
                                                              int max_nodes, float* __restrict__ pe, int64_t ldp,
                                                              int32_t* __restrict__ diam, int32_t* __restrict__ flags,
-                                                             uint32_t* __restrict__ ws) {
+                                                             uint32_t* __restrict__ ws, const int32_t* __restrict__ done) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_changed;
     __shared__ int s_anchor[64];
+    if (done && done[blockIdx.x]) return;                     // a tree: pe_dist_tree_kernel has written it
     const int64_t base = node_off[blockIdx.x];
     const int n = (int)(node_off[blockIdx.x + 1] - base);
     const int W = (max_nodes + 31) >> 5;
@@ -274,9 +397,11 @@ extern "C" int spgnn_anchor_select(const float* fvs_out, int64_t ld, int64_t n_c
 static const size_t kPeDistSmemMax = 160 * 1024;
 static size_t pe_dist_bits_bytes(int64_t max_nodes) { return (size_t)2 * max_nodes * ((max_nodes + 31) / 32) * 4; }
 
+static int64_t pe_done_bytes(int64_t B) { return (B * 4 + 255) & ~(int64_t)255; }
+
 extern "C" int64_t spgnn_pe_dist_ws_bytes(int64_t B, int64_t max_nodes) {
     size_t per = pe_dist_bits_bytes(max_nodes);
-    return per <= kPeDistSmemMax ? 0 : (int64_t)(per * B);
+    return pe_done_bytes(B) + (per <= kPeDistSmemMax ? 0 : (int64_t)(per * B));     // done flags [+ bitsets]
 }
 
 extern "C" int spgnn_pe_dist_init(const int64_t* node_off, const int32_t* in_ptr, const int32_t* in_src,
@@ -286,15 +411,35 @@ extern "C" int spgnn_pe_dist_init(const int64_t* node_off, const int32_t* in_ptr
     SPGNN_REQUIRE(pos_dim > 0 && pos_dim <= 64 && ldp >= pos_dim && max_nodes > 0, "pe_dist: bad shape");
     size_t per = pe_dist_bits_bytes(max_nodes);
     const bool use_ws = per > kPeDistSmemMax;
-    SPGNN_REQUIRE(!use_ws || ws, "pe_dist: workspace required for graphs of %lld nodes", (long long)max_nodes);
+    SPGNN_REQUIRE(ws, "pe_dist: workspace of spgnn_pe_dist_ws_bytes(B, max_nodes) bytes required");
     cudaStream_t st = as_stream(stream);
     SPGNN_CUDA_OK(cudaMemsetAsync(flags, 0, sizeof(int32_t), st));
+    int32_t* done = reinterpret_cast<int32_t*>(ws);
+    uint32_t* bits = use_ws ? reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + pe_done_bytes(B)) : nullptr;
+    // trees (every airway graph) take the anchor-wave kernel; whatever it declines goes to the all-pairs kernel
+    const bool fast = pos_dim < 63 && getenv("SPGNN_PE_ALL_PAIRS") == nullptr;
+    if (fast) {
+        const size_t tsmem = (size_t)max_nodes * (8 + 8 + 4) + 16;
+        SPGNN_REQUIRE(tsmem <= 200 * 1024, "pe_dist: graph of %lld nodes is too large", (long long)max_nodes);
+        static DeviceOnce tattr;
+        if (tsmem > 48 * 1024 && tattr.pending()) {
+            SPGNN_CUDA_OK(cudaFuncSetAttribute(pe_dist_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            tattr.done();
+        }
+        pe_dist_tree_kernel<<<(unsigned)B, kPeThreads, tsmem, st>>>(node_off, in_ptr, in_src, anchors, (int)pos_dim,
+                                                                    pos_enc, ldp, diam, done);
+        SPGNN_LAUNCH_OK();
+    }
     size_t smem = use_ws ? 0 : per;
-    SPGNN_CUDA_OK(cudaFuncSetAttribute(pe_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kPeDistSmemMax));
+    static DeviceOnce attr;
+    if (attr.pending()) {
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(pe_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kPeDistSmemMax));
+        attr.done();
+    }
     pe_dist_kernel<<<(unsigned)B, kPeThreads, smem, st>>>(node_off, in_ptr, in_src, anchors, (int)pos_dim,
-                                                          (int)max_nodes, pos_enc, ldp, diam, flags,
-                                                          use_ws ? (uint32_t*)ws : nullptr);
+                                                          (int)max_nodes, pos_enc, ldp, diam, flags, bits,
+                                                          fast ? done : nullptr);
     SPGNN_LAUNCH_OK();
     return SPGNN_OK;
 }

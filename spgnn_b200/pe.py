@@ -37,7 +37,7 @@ def distance_pos_enc(g, anchors=None, pos_enc_dim=39, store=True, check=True):
     diam = torch.empty(g.batch_size, dtype=torch.int32, device=g.device)
     flags = torch.empty(1, dtype=torch.int32, device=g.device)
     nbytes = int(lib().pe_dist_ws_bytes(g.batch_size, g.max_nodes))
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device) if nbytes else None
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=g.device)
     # nx shortest paths run v -> anchor: propagate along out-edges (same graph when the adjacency is symmetric)
     lib().pe_dist_init(ptr(g.node_off), ptr(g.out_ptr), ptr(g.out_dst), ptr(anchors), g.batch_size, pos_enc_dim,
                        g.max_nodes, ptr(pe), pe.stride(0), ptr(diam), ptr(flags), ptr(ws), stream())

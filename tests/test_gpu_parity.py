@@ -782,3 +782,28 @@ def test_dormant_pe_extras_and_graph_api_leftovers_vs_oracle(mods):
         assert abs(float(d1) - float(d0)) < 1e-5 * abs(float(d0)) and abs(float(c1) - float(c0)) <= 1e-4 * max(abs(float(c0)), 1e-6)
         (d1 + c1).backward()
         assert torch.isfinite(pd.grad).all()
+
+
+def test_distance_pe_tree_kernel_equals_all_pairs_kernel_and_oracle(mods, monkeypatch):
+    """spgnn_pe_dist_init: the anchor-wave + double-BFS kernel that trees take gives bit-identical encodings and
+    diameters to the all-pairs kernel (SPGNN_PE_ALL_PAIRS=1) and to the oracle's hop matrix; a graph with a cycle
+    in the same batch is declined by the tree kernel and still comes out right; single-node graphs included."""
+    rng = np.random.default_rng(21)
+    adjs = [_random_tree_adj(n, mc, rng) for n, mc in ((301, 2), (64, 5), (1, 2), (37, 3), (150, 2), (2, 2))]
+    cyc = _random_tree_adj(80, 2, rng)
+    cyc[5, 70] = cyc[70, 5] = 1                                  # one extra edge: a cycle, diameter by all pairs
+    adjs.insert(2, cyc)
+    g = mods["sg"].batch_from_adjs(adjs)
+    anchors = torch.stack([torch.from_numpy(rng.integers(0, a.shape[0], 39).astype(np.int32)) for a in adjs]).cuda()
+    pe_fast, d_fast = mods["spe"].distance_pos_enc(g, anchors, store=False)
+    monkeypatch.setenv("SPGNN_PE_ALL_PAIRS", "1")
+    pe_all, d_all = mods["spe"].distance_pos_enc(g, anchors, store=False)
+    monkeypatch.delenv("SPGNN_PE_ALL_PAIRS")
+    assert torch.equal(pe_fast, pe_all) and torch.equal(d_fast, d_all)
+    off = g.node_off.tolist()
+    for i, a in enumerate(adjs):
+        if a.shape[0] == 1:
+            assert float(pe_fast[off[i]].abs().max()) == 0.0 and int(d_fast[i]) == 0
+            continue
+        ref, _, diam = mods["ope"].dist_pos_enc(a, anchors[i].cpu().tolist())
+        assert int(d_fast[i]) == diam and np.array_equal(pe_fast[off[i]:off[i + 1]].cpu().numpy(), ref), i
