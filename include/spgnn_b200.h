@@ -150,6 +150,14 @@ int64_t spgnn_planes_linear_bwd_input_ws(int64_t N, int64_t K);
 int spgnn_planes_linear_bwd_input(const uint16_t* dC, int64_t lddc, int64_t ps, const float* W, int64_t ldw,
                                   int64_t k_off, float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K,
                                   void* ws, int64_t ws_bytes, void* stream);
+/* Same, with the feat_drop mask of the consuming layer folded into the epilogue: dA is the gradient of the DROPPED
+ * input, dA[r, c] *= keep(r, c) / (1 - drop_p), keep from the plane producers' hash convention (16 bits per element,
+ * chunk index r * concat_chunks + (k_off + c) / 4, k_off % 4 == 0; concat_chunks <= 0: ceil((k_off + K) / 4)).  drop_p == 0: identical to the call above.
+ * The producer layer's backward then reads an already-masked gradient source (its GSrc.drop_p = 0). */
+int spgnn_planes_linear_bwd_input_masked(const uint16_t* dC, int64_t lddc, int64_t ps, const float* W, int64_t ldw,
+                                         int64_t k_off, float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K,
+                                         float drop_p, uint64_t seed, int64_t concat_chunks,
+                                         void* ws, int64_t ws_bytes, void* stream);
 int64_t spgnn_planes_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K1, int64_t K2);
 int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, int64_t psc,
                                    const uint16_t* X1, int64_t ldx1, int64_t psx1, int64_t K1,

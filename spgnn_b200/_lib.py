@@ -71,7 +71,7 @@ class _Lib:
         if "spgnn_" + name not in self._status:
             return fn
 
-        def call(*args, _key=None):
+        def call(*args, _key=None, _name=None):
             prof = self.profile
             if prof is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -81,7 +81,7 @@ class _Lib:
                 raise SpgnnError(f"spgnn_{name} failed ({rc}): {self.last_error()}")
             if prof is not None:
                 e1.record()
-                prof.append((name, _key, e0, e1))
+                prof.append((_name or name, _key, e0, e1))
         return call
 
 

@@ -17,6 +17,7 @@
 //
 // Applies when F % 64 == 0, no head mean, every degree <= 4 and the largest graph has <= 384 nodes; everything else
 // takes the chunk kernels of gat_layer.cu.
+#include <stdlib.h>
 #include "layer_util.cuh"
 
 namespace spgnn {
@@ -29,8 +30,10 @@ constexpr int kBoxRows = 32;       // TMA box: 32 rows x 32 columns
 constexpr int kThreads = 512;
 constexpr int kQW = kThreads / 8;  // 64 quarter-warps; a quarter-warp owns one node of the slice (8 lanes x float4)
 constexpr int kPer = 6;            // nodes per quarter-warp per slice
-constexpr int kBatch = 3;          // rounds whose shared-memory gathers are issued together (kPer % kBatch == 0)
-constexpr int kMaxNodes = kQW * kPer;
+constexpr int kBatch = 3;          // forward: rounds whose shared-memory gathers are issued together
+constexpr int kBatchBwd = 4;       // backward source side (same-box A/B at 640 threads x 4 rounds: 2 / 3 / 4 rounds per
+                                   // batch -> 1.90 / 1.86 / 1.79 ms per launch, profiles/r02_tree_bwd_variants.txt)
+constexpr int kMaxNodes = kQW * kPer;   // 384: every backward launch shape below covers it as well
 constexpr size_t kSmemLimit = 232448;
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
@@ -110,8 +113,9 @@ static size_t fwd_smem_bytes(int nmax, int H, int nstages) {
     return 128 + (size_t)nmax * (4 + 8 + H * 16) + 128 + (size_t)nstages * nmax * kCS * 4 + 128;
 }
 
-template <int ACT, int KPER>
-__global__ void __launch_bounds__(kThreads, 1) gat_tree_fwd_kernel(const __grid_constant__ CUtensorMap zmap, const TArgs t) {
+template <int ACT, int THREADS, int KPER>
+__global__ void __launch_bounds__(THREADS, 1) gat_tree_fwd_kernel(const __grid_constant__ CUtensorMap zmap, const TArgs t) {
+    constexpr int kThreads = THREADS, kQW = THREADS / 8;
     extern __shared__ __align__(128) uint8_t smem[];
     const Args& a = t.a;
     const int H = a.H, F = a.F;
@@ -265,7 +269,7 @@ struct BSmem {
     float* sb;                     // [H*F]
     float* zs; float* gs;
 };
-__device__ __forceinline__ BSmem carve_b(uint8_t* base, int nmax, int H, int HF, int nstages) {
+__device__ __forceinline__ BSmem carve_b(uint8_t* base, int nmax, int H, int HF, int nstages, int nwarps) {
     BSmem s;
     s.full = reinterpret_cast<uint64_t*>(base);
     s.deg = reinterpret_cast<int*>(base + 128);
@@ -280,14 +284,14 @@ __device__ __forceinline__ BSmem carve_b(uint8_t* base, int nmax, int H, int HF,
     s.ow = s.dd + (size_t)nmax * H * 4;
     s.ds = s.ow + (size_t)nmax * H * 4;
     s.part = s.ds + (size_t)nmax * H * 4;
-    s.sb = s.part + (kThreads / 32) * kCS;
+    s.sb = s.part + nwarps * kCS;
     uintptr_t z = reinterpret_cast<uintptr_t>(s.sb + HF);
     s.zs = reinterpret_cast<float*>((z + 127) & ~(uintptr_t)127);
     s.gs = s.zs + (size_t)nstages * nmax * kCS;
     return s;
 }
-static size_t bwd_smem_bytes(int nmax, int H, int HF, int nstages) {
-    return 128 + (size_t)nmax * (12 + 24 + 5 * H * 16) + (size_t)(kThreads / 32) * kCS * 4 + (size_t)HF * 4 + 128 +
+static size_t bwd_smem_bytes(int nmax, int H, int HF, int nstages, int nwarps) {
+    return 128 + (size_t)nmax * (12 + 24 + 5 * H * 16) + (size_t)nwarps * kCS * 4 + (size_t)HF * 4 + 128 +
            (size_t)(nstages + 1) * nmax * kCS * 4 + 128;
 }
 
@@ -307,16 +311,21 @@ __device__ __forceinline__ float4 act_slope4(float4 p, int act) {
     return make_float4(act_slope<ACT>(p.x, act), act_slope<ACT>(p.y, act), act_slope<ACT>(p.z, act), act_slope<ACT>(p.w, act));
 }
 
-// NG gradient sources; ACT: activation known at compile time (0 = read it from the arguments); KPER: rounds of 64
-// nodes a slice takes (5 covers trees of up to 320 nodes and frees 4 * (1 + NG) prefetch registers)
-template <int NG, int ACT, int KPER>
-__global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_constant__ CUtensorMap zmap, const TArgs t) {
+// NG gradient sources; ACT: activation known at compile time (0 = read it from the arguments); THREADS / 8 nodes are
+// taken per round and a slice takes KPER rounds; PF: how many rounds ahead a node's own-row operands (residual
+// projection, gradient sources) are loaded into registers.  PF == KPER is the first generation of this kernel
+// (512 threads, everything of the next slice loaded a whole slice ahead: 4 * KPER * (1 + NG) registers, which pinned
+// the kernel at 128 registers x 16 warps); PF = 2 with 896 threads keeps 8 * (1 + NG) prefetch registers and lets
+// 28 warps share the issue slots (the ncu source view showed neither DRAM nor issue slots saturated at 16 warps).
+template <int NG, int ACT, int THREADS, int KPER, int PF>
+__global__ void __launch_bounds__(THREADS, 1) gat_tree_bwd_kernel(const __grid_constant__ CUtensorMap zmap, const TArgs t) {
+    constexpr int kThreads = THREADS, kQW = THREADS / 8;
+    static_assert(PF >= 1 && PF <= KPER, "prefetch depth");
     extern __shared__ __align__(128) uint8_t smem[];
     const Args& a = t.a;
     const int H = a.H, F = a.F, HF = H * F;
-    const BSmem st = carve_b(smem, t.nmax, H, HF, t.nstages);
+    const BSmem st = carve_b(smem, t.nmax, H, HF, t.nstages, THREADS / 32);
     const int l8 = threadIdx.x & 7, qw = threadIdx.x >> 3;
-    const unsigned qmask = 0xFFu << (threadIdx.x & 24);
     const uint32_t zs_u32 = smem_u32(st.zs), gs_u32 = smem_u32(st.gs);
     const uint32_t stage_bytes = (uint32_t)t.nmax * kCS * 4;
     const bool has_res = a.res_mode == 1;
@@ -341,21 +350,23 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
                 issue_slice(&zmap, smem_u32(&st.full[1]), zs_u32 + stage_bytes, nxt.n0, nxt.n, nxt.s * kCS);
         }
     }
-    // own-row operands of the item about to be computed: residual projection and the raw gradient sources
-    float4 r[KPER], g[NG][KPER];
+    // own-row operands (residual projection, raw gradient sources) of the rounds about to be computed: a ring of PF
+    // rounds in registers, round k of an item lives in slot k % PF (every index below is a compile-time constant)
+    float4 r[PF], g[NG][PF];
     float4 bv = zero4();
-    auto load_own = [&](const Cursor& it) {
+    auto load_round = [&](const Cursor& it, int k, float4& r_, float4 (&g_)[NG][PF], int slot) {
+        const int i = qw + k * kQW;
+        const bool on = i < it.n;
+        const int64_t v = it.n0 + i;
+        const int c = it.s * kCS + l8 * 4;
+        r_ = (has_res && on) ? ldg4(a.Y + v * a.ldy + a.res_off + c) : zero4();
+#pragma unroll
+        for (int q = 0; q < NG; ++q) g_[q][slot] = on ? ldg4(a.gs[q].g + v * a.gs[q].ld + c) : zero4();
+    };
+    auto load_own = [&](const Cursor& it) {        // the first PF rounds of an item
         if (a.bias) bv = ldg4(a.bias + it.s * kCS + l8 * 4);
 #pragma unroll
-        for (int k = 0; k < KPER; ++k) {
-            const int i = qw + k * kQW;
-            const bool on = i < it.n;
-            const int64_t v = it.n0 + i;
-            const int c = it.s * kCS + l8 * 4;
-            r[k] = (has_res && on) ? ldg4(a.Y + v * a.ldy + a.res_off + c) : zero4();
-#pragma unroll
-            for (int q = 0; q < NG; ++q) g[q][k] = on ? ldg4(a.gs[q].g + v * a.gs[q].ld + c) : zero4();
-        }
+        for (int k = 0; k < PF; ++k) load_round(it, k, r[k], g, k);
     };
     if (cur.valid(t)) load_own(cur);
 
@@ -413,19 +424,24 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
 #pragma unroll
         for (int k = 0; k < KPER; ++k) {
             const int i = qw + k * kQW;
+            const float4 rk = r[k % PF];
+            float4 gk[NG];
+#pragma unroll
+            for (int q = 0; q < NG; ++q) gk[q] = g[q][k % PF];
+            if (k + PF < KPER) load_round(cur, k + PF, r[k % PF], g, k % PF);     // in flight for PF rounds
             if (i < n) {
                 const int64_t v = n0 + i;
                 const short4s nb = st.nb[i];
                 const float4 w = *reinterpret_cast<const float4*>(st.w + (i * H + h) * 4);
                 const float4 z0 = lds4(zs + nb.x * (kCS * 4)), z1 = lds4(zs + nb.y * (kCS * 4));
                 const float4 z2 = lds4(zs + nb.z * (kCS * 4)), z3 = lds4(zs + nb.w * (kCS * 4));
-                float4 acc = add4(r[k], bv);
+                float4 acc = add4(rk, bv);
                 acc = fma4(w.x, z0, acc); acc = fma4(w.y, z1, acc); acc = fma4(w.z, z2, acc); acc = fma4(w.w, z3, acc);
                 float4 go = zero4();
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
                     const GSrc& gq_ = a.gs[q];
-                    go = add4(go, drop4(g[q][k], gq_.thr, gq_.scale, gq_.seed,
+                    go = add4(go, drop4(gk[q], gq_.thr, gq_.scale, gq_.seed,
                                         (uint64_t)v * (uint64_t)gq_.nch + (uint64_t)(gq_.ch_off + (c >> 2))));
                 }
                 const float4 gq = mul4(go, act_slope4<ACT>(acc, a.act));
@@ -433,8 +449,9 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
                 if (has_res) store_planes4(a.dY + v * a.dld + a.res_off + c, a.dps, gq);
                 bsum = add4(bsum, gq);
                 float d0 = dot4(gq, z0), d1 = dot4(gq, z1), d2 = dot4(gq, z2), d3 = dot4(gq, z3);
+                const unsigned qmask = 0xFFu << (threadIdx.x & 24);
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {      // quarter-warps of one warp may sit on different sides of i < n
+                for (int o = 1; o < 8; o <<= 1) {
                     d0 += __shfl_xor_sync(qmask, d0, o); d1 += __shfl_xor_sync(qmask, d1, o);
                     d2 += __shfl_xor_sync(qmask, d2, o); d3 += __shfl_xor_sync(qmask, d3, o);
                 }
@@ -479,8 +496,8 @@ __global__ void __launch_bounds__(kThreads, 1) gat_tree_bwd_kernel(const __grid_
         // (the per-round chain list -> gather -> FMA -> store left the 4 warps of a scheduler waiting on shared-memory
         // latency: 18 % of this kernel's stall samples sat on these lines, profiles/r01_ncu_tree_bwd_source.txt).
 #pragma unroll
-        for (int k0 = 0; k0 < KPER; k0 += kBatch) {
-            constexpr int kB = kBatch;
+        for (int k0 = 0; k0 < KPER; k0 += kBatchBwd) {
+            constexpr int kB = kBatchBwd;
             const int nb_ = KPER - k0 < kB ? KPER - k0 : kB;   // rounds in this batch (compile-time after unrolling)
             if ((qw & ~3) + k0 * kQW < n) {                    // warp-uniform: this warp has a node in round k0
                 short4s nb[kB];
@@ -610,6 +627,49 @@ static int setup(TArgs& t, const Args& a, const spgnn_gat_layer* L, CUtensorMap*
     return make_rows_map(zmap, a.Y, a.N, (int64_t)a.H * a.F, a.ldy);
 }
 
+template <int ACT, int THREADS, int KPER>
+static int launch_fwd_cfg(const CUtensorMap& zmap, TArgs& t, const Args& a, const spgnn_gat_layer* L, cudaStream_t st,
+                          bool* handled) {
+    t.nstages = fwd_smem_bytes(t.nmax, a.H, 2) <= kSmemLimit ? 2 : 1;
+    const size_t smem = fwd_smem_bytes(t.nmax, a.H, t.nstages);
+    if (smem > kSmemLimit) return SPGNN_OK;
+    auto fn = gat_tree_fwd_kernel<ACT, THREADS, KPER>;
+    static DeviceOnce attr;
+    if (attr.pending()) {
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        attr.done();
+    }
+    const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
+    fn<<<grid, THREADS, smem, st>>>(zmap, t);
+    SPGNN_LAUNCH_OK();
+    *handled = true;
+    return SPGNN_OK;
+}
+
+// Launch shape of the forward: 512 threads x 5-6 rounds of 64 nodes.  The shapes that help the backward (640 x 4,
+// 608 x 4, 896 x 3, 1024 x 3) measured within noise or slower here (0.91 - 0.95 vs 0.92 - 1.04 ms per launch,
+// profiles/r02_tree_bwd_variants.txt); SPGNN_TREE_FWD=1 selects 896 x 3-4 for A/B runs.
+static int fwd_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPGNN_TREE_FWD");
+        v = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return v;
+}
+
+template <int ACT>
+static int launch_fwd_act(const CUtensorMap& zmap, TArgs& t, const Args& a, const spgnn_gat_layer* L, cudaStream_t st,
+                          bool* handled) {
+    const int64_t n = L->max_nodes;
+    if (fwd_variant() == 1) {
+        if (n <= 3 * 112) return launch_fwd_cfg<ACT, 896, 3>(zmap, t, a, L, st, handled);
+        return launch_fwd_cfg<ACT, 896, 4>(zmap, t, a, L, st, handled);
+    }
+    if (n <= 5 * 64) return launch_fwd_cfg<ACT, 512, 5>(zmap, t, a, L, st, handled);
+    return launch_fwd_cfg<ACT, 512, 6>(zmap, t, a, L, st, handled);
+}
+
 // returns SPGNN_OK and sets *handled when the tree kernel ran
 int launch_fwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* handled) {
     *handled = false;
@@ -618,26 +678,72 @@ int launch_fwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* h
     CUtensorMap zmap;
     int rc = setup(t, a, L, &zmap);
     if (rc) return rc;
-    t.nstages = fwd_smem_bytes(t.nmax, a.H, 2) <= kSmemLimit ? 2 : 1;
-    const size_t smem = fwd_smem_bytes(t.nmax, a.H, t.nstages);
+    if (a.act == SPGNN_ACT_ELU) return launch_fwd_act<SPGNN_ACT_ELU>(zmap, t, a, L, st, handled);
+    if (a.act == SPGNN_ACT_TANH) return launch_fwd_act<SPGNN_ACT_TANH>(zmap, t, a, L, st, handled);
+    return launch_fwd_act<0>(zmap, t, a, L, st, handled);
+}
+
+// one launch configuration of the backward: threads per CTA, rounds per slice, prefetch depth
+template <int NG, int ACT, int THREADS, int KPER, int PF>
+static int launch_bwd_cfg(const CUtensorMap& zmap, TArgs& t, const Args& a, const spgnn_gat_layer* L, cudaStream_t st,
+                          bool* handled) {
+    const int HF = a.H * a.F, nwarps = THREADS / 32;
+    t.nstages = bwd_smem_bytes(t.nmax, a.H, HF, 2, nwarps) <= kSmemLimit ? 2 : 1;
+    const size_t smem = bwd_smem_bytes(t.nmax, a.H, HF, t.nstages, nwarps);
     if (smem > kSmemLimit) return SPGNN_OK;
-    using FwdFn = void (*)(const CUtensorMap, const TArgs);
-    static const FwdFn table[3][2] = {{gat_tree_fwd_kernel<0, 5>, gat_tree_fwd_kernel<0, 6>},
-                                      {gat_tree_fwd_kernel<SPGNN_ACT_ELU, 5>, gat_tree_fwd_kernel<SPGNN_ACT_ELU, 6>},
-                                      {gat_tree_fwd_kernel<SPGNN_ACT_TANH, 5>, gat_tree_fwd_kernel<SPGNN_ACT_TANH, 6>}};
+    auto fn = gat_tree_bwd_kernel<NG, ACT, THREADS, KPER, PF>;
     static DeviceOnce attr;
     if (attr.pending()) {
-        for (auto& per_act : table)
-            for (FwdFn fn : per_act)
-                SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         attr.done();
     }
     const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
-    const int act_i = a.act == SPGNN_ACT_ELU ? 1 : (a.act == SPGNN_ACT_TANH ? 2 : 0);
-    table[act_i][L->max_nodes <= 5 * kQW ? 0 : 1]<<<grid, kThreads, smem, st>>>(zmap, t);
+    fn<<<grid, THREADS, smem, st>>>(zmap, t);
     SPGNN_LAUNCH_OK();
+    if (L->dbias) {
+        tree_dbias_reduce_kernel<<<(unsigned)ceil_div(HF, 128), 128, 0, st>>>(a.dbias_ws, grid, HF, L->dbias);
+        SPGNN_LAUNCH_OK();
+    }
     *handled = true;
     return SPGNN_OK;
+}
+
+// Launch shape of the backward.  Default: 640 threads (20 warps, 96 registers), a slice in 4 rounds of 80 nodes (5 for
+// graphs of up to 400 nodes), own rows loaded 3 (2) rounds ahead.  Same-box A/Bs on 4096 trees of 301 nodes
+// (profiles/r02_tree_bwd_variants.txt), ms per launch averaged over the step's six launches:
+//   512 x 5 rounds, whole-slice prefetch (first generation, 128 registers)  2.04 - 2.09
+//   640 x 4, 2 rounds ahead 1.83 - 1.88   |  640 x 4, whole-slice 1.98 - 2.01  |  608 x 4 1.93  |  832 x 3 1.93
+//   896 x 3 1.95 - 1.98  |  1024 x 3 (64 registers) 2.10 - 2.14: more warps do not help, the rounds of a slice must
+//   divide the tree evenly (301 = 80 + 80 + 80 + 61) because every slice ends in a block barrier.
+// SPGNN_TREE_BWD = 0 (first generation) / 1 (896 x 3) / 9 (640 x 4, 2 rounds ahead) keep the alternatives reachable.
+static int bwd_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPGNN_TREE_BWD");
+        v = e ? atoi(e) : 3;
+        if (v != 0 && v != 1 && v != 9) v = 3;
+    }
+    return v;
+}
+
+template <int NG, int ACT>
+static int launch_bwd_act(const CUtensorMap& zmap, TArgs& t, const Args& a, const spgnn_gat_layer* L, cudaStream_t st,
+                          bool* handled) {
+    const int64_t n = L->max_nodes;
+    switch (bwd_variant()) {
+        case 0:
+            if (n <= 5 * 64) return launch_bwd_cfg<NG, ACT, 512, 5, 5>(zmap, t, a, L, st, handled);
+            return launch_bwd_cfg<NG, ACT, 512, 6, 6>(zmap, t, a, L, st, handled);
+        case 1:
+            if (n <= 3 * 112) return launch_bwd_cfg<NG, ACT, 896, 3, 2>(zmap, t, a, L, st, handled);
+            return launch_bwd_cfg<NG, ACT, 896, 4, 2>(zmap, t, a, L, st, handled);
+        case 9:
+            if (n <= 4 * 80) return launch_bwd_cfg<NG, ACT, 640, 4, 2>(zmap, t, a, L, st, handled);
+            return launch_bwd_cfg<NG, ACT, 640, 5, 2>(zmap, t, a, L, st, handled);
+        default:
+            if (n <= 4 * 80) return launch_bwd_cfg<NG, ACT, 640, 4, 3>(zmap, t, a, L, st, handled);
+            return launch_bwd_cfg<NG, ACT, 640, 5, 2>(zmap, t, a, L, st, handled);
+    }
 }
 
 int launch_bwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* handled) {
@@ -647,38 +753,14 @@ int launch_bwd(const Args& a, const spgnn_gat_layer* L, cudaStream_t st, bool* h
     CUtensorMap zmap;
     int rc = setup(t, a, L, &zmap);
     if (rc) return rc;
-    const int HF = a.H * a.F;
-    t.nstages = bwd_smem_bytes(t.nmax, a.H, HF, 2) <= kSmemLimit ? 2 : 1;
-    const size_t smem = bwd_smem_bytes(t.nmax, a.H, HF, t.nstages);
-    if (smem > kSmemLimit) return SPGNN_OK;
-    using BwdFn = void (*)(const CUtensorMap, const TArgs);
-    // [NG - 1][ACT: 0 generic, 1 ELU, 2 tanh][KPER - 5]
-    static const BwdFn table[2][3][2] = {
-        {{gat_tree_bwd_kernel<1, 0, 5>, gat_tree_bwd_kernel<1, 0, 6>},
-         {gat_tree_bwd_kernel<1, SPGNN_ACT_ELU, 5>, gat_tree_bwd_kernel<1, SPGNN_ACT_ELU, 6>},
-         {gat_tree_bwd_kernel<1, SPGNN_ACT_TANH, 5>, gat_tree_bwd_kernel<1, SPGNN_ACT_TANH, 6>}},
-        {{gat_tree_bwd_kernel<2, 0, 5>, gat_tree_bwd_kernel<2, 0, 6>},
-         {gat_tree_bwd_kernel<2, SPGNN_ACT_ELU, 5>, gat_tree_bwd_kernel<2, SPGNN_ACT_ELU, 6>},
-         {gat_tree_bwd_kernel<2, SPGNN_ACT_TANH, 5>, gat_tree_bwd_kernel<2, SPGNN_ACT_TANH, 6>}}};
-    static DeviceOnce attr;
-    if (attr.pending()) {
-        for (auto& per_ng : table)
-            for (auto& per_act : per_ng)
-                for (BwdFn fn : per_act)
-                    SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        attr.done();
+    if (a.n_g == 1) {
+        if (a.act == SPGNN_ACT_ELU) return launch_bwd_act<1, SPGNN_ACT_ELU>(zmap, t, a, L, st, handled);
+        if (a.act == SPGNN_ACT_TANH) return launch_bwd_act<1, SPGNN_ACT_TANH>(zmap, t, a, L, st, handled);
+        return launch_bwd_act<1, 0>(zmap, t, a, L, st, handled);
     }
-    const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
-    const int act_i = a.act == SPGNN_ACT_ELU ? 1 : (a.act == SPGNN_ACT_TANH ? 2 : 0);
-    const int kper_i = L->max_nodes <= 5 * kQW ? 0 : 1;
-    table[a.n_g - 1][act_i][kper_i]<<<grid, kThreads, smem, st>>>(zmap, t);
-    SPGNN_LAUNCH_OK();
-    if (L->dbias) {
-        tree_dbias_reduce_kernel<<<(unsigned)ceil_div(HF, 128), 128, 0, st>>>(a.dbias_ws, grid, HF, L->dbias);
-        SPGNN_LAUNCH_OK();
-    }
-    *handled = true;
-    return SPGNN_OK;
+    if (a.act == SPGNN_ACT_ELU) return launch_bwd_act<2, SPGNN_ACT_ELU>(zmap, t, a, L, st, handled);
+    if (a.act == SPGNN_ACT_TANH) return launch_bwd_act<2, SPGNN_ACT_TANH>(zmap, t, a, L, st, handled);
+    return launch_bwd_act<2, 0>(zmap, t, a, L, st, handled);
 }
 
 }  // namespace tree

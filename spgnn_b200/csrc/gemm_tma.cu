@@ -59,7 +59,18 @@ struct NtArgs {
     int BN, nt_n; int64_t nt_m;
     int kb1, kb2;
     int stages, stage_bytes;
+    // optional dropout mask on the OUTPUT (dX of a layer whose input went through feat_drop): 16 hash bits per
+    // element, chunk index = row * mnch + col / 4 -- the convention of every plane producer (split_planes_kernel)
+    uint32_t mthr; float mscale; uint64_t mseed; int64_t mnch, moff;
 };
+__device__ __forceinline__ float4 nt_mask4(const NtArgs& g, float4 x, int64_t row, int col) {
+    const uint64_t h = chunk_hash(g.mseed, (uint64_t)row * (uint64_t)g.mnch + (uint64_t)(g.moff + (col >> 2)));
+    x.x = ((uint32_t)(h) & 0xFFFFu) >= g.mthr ? x.x * g.mscale : 0.f;
+    x.y = ((uint32_t)(h >> 16) & 0xFFFFu) >= g.mthr ? x.y * g.mscale : 0.f;
+    x.z = ((uint32_t)(h >> 32) & 0xFFFFu) >= g.mthr ? x.z * g.mscale : 0.f;
+    x.w = ((uint32_t)(h >> 48) & 0xFFFFu) >= g.mthr ? x.w * g.mscale : 0.f;
+    return x;
+}
 struct NtShared {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
@@ -145,9 +156,16 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                 const int nrow = (int)max((int64_t)0, min((int64_t)8, (g.M - row0 + 3) / 4));
                 const uint32_t sp = stg + (rsub * kStgLd + cc) * 4;
                 if (plain && vec_ok && c0 + 32 <= ncols) {
+                    if (g.mthr) {
 #pragma unroll
-                    for (int itr = 0; itr < 8; ++itr)
-                        if (itr < nrow) st4(q + itr * qstep, ld_shared4(sp + itr * (4 * kStgLd * 4)));
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nrow)
+                                st4(q + itr * qstep, nt_mask4(g, ld_shared4(sp + itr * (4 * kStgLd * 4)), row0 + 4 * itr, col));
+                    } else {
+#pragma unroll
+                        for (int itr = 0; itr < 8; ++itr)
+                            if (itr < nrow) st4(q + itr * qstep, ld_shared4(sp + itr * (4 * kStgLd * 4)));
+                    }
                 } else {
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (g.bias) {
@@ -163,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                         x.y = act_fwd(x.y + bv.y, g.act, g.slope);
                         x.z = act_fwd(x.z + bv.z, g.act, g.slope);
                         x.w = act_fwd(x.w + bv.w, g.act, g.slope);
+                        if (g.mthr) x = nt_mask4(g, x, row0 + 4 * itr, col);
                         float* qq = q + itr * qstep;
                         if (vec_ok && nvalid >= 4) st4(qq, x);
                         else {
@@ -898,7 +917,8 @@ static unsigned split_grid(int64_t total) {
 // C = [A1|A2] * Bplanes^T with Bplanes [N, ldb] already split (hi at Bhi, lo at Bhi + N*ldb)
 static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t K1, const __nv_bfloat16* A2,
                      int64_t lda2, int64_t ps2, int64_t K2, const __nv_bfloat16* Bhi, int64_t ldb, const float* bias,
-                     int act, float slope, float* C, int64_t ldc, int64_t M, int64_t N, cudaStream_t st) {
+                     int act, float slope, float* C, int64_t ldc, int64_t M, int64_t N, cudaStream_t st,
+                     float mask_p = 0.f, uint64_t mask_seed = 0, int64_t mask_chunks = 0, int64_t mask_chunk_off = 0) {
     static DeviceOnce attr;
     static int max_clusters = 0;             // co-resident 2-CTA clusters (0: cluster launches unavailable)
     if (attr.pending()) {
@@ -937,6 +957,9 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
                  : make_planes_map(&maps.b, Bhi, N, ldb, ldb, N * ldb, BK, a.BN);
     if (rc) return rc;
     a.bias = bias; a.act = act; a.slope = slope; a.C = C; a.ldc = ldc; a.M = M; a.N = (int)N;
+    a.mthr = mask_p > 0.f ? (uint32_t)(mask_p * 65536.f + 0.5f) : 0u;
+    a.mscale = mask_p > 0.f ? 1.f / (1.f - mask_p) : 1.f;
+    a.mseed = mask_seed; a.mnch = mask_chunks > 0 ? mask_chunks : (N + 3) / 4; a.moff = mask_chunk_off;
     a.nt_m = ceil_div(M, BM);
     a.kb1 = (int)ceil_div(K1, BK);
     a.kb2 = (A2 && K2 > 0) ? (int)ceil_div(K2, BK) : 0;
@@ -1113,7 +1136,19 @@ extern "C" int64_t spgnn_planes_linear_bwd_input_ws(int64_t N, int64_t K) {
 extern "C" int spgnn_planes_linear_bwd_input(const uint16_t* dC, int64_t lddc, int64_t ps, const float* W, int64_t ldw,
                                              int64_t k_off, float* dA, int64_t ldda, int64_t M, int64_t N, int64_t K,
                                              void* ws, int64_t ws_bytes, void* stream) {
+    return spgnn_planes_linear_bwd_input_masked(dC, lddc, ps, W, ldw, k_off, dA, ldda, M, N, K, 0.f, 0, 0, ws, ws_bytes,
+                                                stream);
+}
+
+// ... followed by the feat_drop mask of the layer whose (dropped) input dA is the gradient of: dA *= mask / (1 - p),
+// mask chunk index = row * concat_chunks + (k_off + col) / 4 (dA column c is input column k_off + c)
+extern "C" int spgnn_planes_linear_bwd_input_masked(const uint16_t* dC, int64_t lddc, int64_t ps, const float* W,
+                                                    int64_t ldw, int64_t k_off, float* dA, int64_t ldda, int64_t M,
+                                                    int64_t N, int64_t K, float drop_p, uint64_t seed,
+                                                    int64_t concat_chunks, void* ws, int64_t ws_bytes, void* stream) {
     SPGNN_REQUIRE(dC && W && dA && ws && M > 0 && N > 0 && K > 0, "planes_linear_bwd_input: bad argument");
+    SPGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "planes_linear_bwd_input: dropout p");
+    SPGNN_REQUIRE(drop_p == 0.f || k_off % 4 == 0, "planes_linear_bwd_input: a masked output needs k_off %% 4 == 0");
     SPGNN_REQUIRE(ldw >= k_off + K && ldda >= K, "planes_linear_bwd_input: leading dimension too small");
     SPGNN_REQUIRE(ws_bytes >= spgnn_planes_linear_bwd_input_ws(N, K), "planes_linear_bwd_input: workspace too small");
     cudaStream_t st = as_stream(stream);
@@ -1123,7 +1158,7 @@ extern "C" int spgnn_planes_linear_bwd_input(const uint16_t* dC, int64_t lddc, i
                                                             hi + K * np, np);
     SPGNN_LAUNCH_OK();
     return launch_nt(reinterpret_cast<const __nv_bfloat16*>(dC), lddc, ps, N, nullptr, 0, 0, 0, hi, np, nullptr, 0, 0.f,
-                     dA, ldda, M, K, st);
+                     dA, ldda, M, K, st, drop_p, seed, concat_chunks > 0 ? concat_chunks : (k_off + K + 3) / 4, k_off / 4);
 }
 
 namespace {

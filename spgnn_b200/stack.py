@@ -16,6 +16,7 @@ PyTorch is plumbing here: memory, streams, the autograd hook-up of the parameter
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -81,6 +82,10 @@ class _Wide(ctypes.Structure):
 WIDE_OUTPUT_LAYER = True
 # One CTA per graph with the graph's rows staged in shared memory (spgnn_gat_layer.node_off).  Off: chunk kernels.
 TREE_KERNELS = True
+# The feat_drop mask of a layer's input is applied to the gradient in that layer's dX GEMM epilogue (tensor-bound, idle
+# issue slots) instead of in the producing layer's aggregation backward (issue-bound: the mask hash was a quarter of
+# its destination-side instructions).  Off (SPGNN_FOLD_MASK=0): the aggregation backward masks its gradient sources.
+FOLD_MASK = os.environ.get("SPGNN_FOLD_MASK", "1") != "0"
 
 _checked = False
 
@@ -170,15 +175,22 @@ def planes_linear(A1: Planes, W, bias=None, act=0, slope=0.0, A2: Planes | None 
     return C
 
 
-def planes_linear_bwd_input(dC: Planes, W, K, k_off=0, out=None):
-    """fp32 [M, K] = dC @ W[:, k_off:k_off+K]"""
+def planes_linear_bwd_input(dC: Planes, W, K, k_off=0, out=None, drop_p=0.0, seed=0, concat_chunks=0):
+    """fp32 [M, K] = dC @ W[:, k_off:k_off+K]; ``drop_p`` > 0: times the feat_drop mask (and 1 / (1 - p)) of the layer
+    whose dropped input this is the gradient of — the mask every plane producer derives from (seed, row, column
+    chunk), applied here in the GEMM epilogue so the producing layer's backward reads a finished gradient."""
     W = ops._rows(W)
     M, N = dC.rows, dC.cols
     dA = ops.empty_padded(M, K, W.device) if out is None else out
     L = lib()
     ws = _ws(L.planes_linear_bwd_input_ws(N, K), W.device)
-    L.planes_linear_bwd_input(dC.ptr(), dC.ld, dC.ps, ptr(W), W.stride(0), k_off, ptr(dA), dA.stride(0), M, N, K,
-                              ptr(ws), ws.numel(), stream(), _key=("flops", 2.0 * M * N * K))
+    if drop_p > 0.0:
+        L.planes_linear_bwd_input_masked(dC.ptr(), dC.ld, dC.ps, ptr(W), W.stride(0), k_off, ptr(dA), dA.stride(0), M,
+                                         N, K, float(drop_p), int(seed), int(concat_chunks), ptr(ws), ws.numel(),
+                                         stream(), _key=("flops", 2.0 * M * N * K), _name="planes_linear_bwd_input")
+    else:
+        L.planes_linear_bwd_input(dC.ptr(), dC.ld, dC.ps, ptr(W), W.stride(0), k_off, ptr(dA), dA.stride(0), M, N, K,
+                                  ptr(ws), ws.numel(), stream(), _key=("flops", 2.0 * M * N * K))
     return dA
 
 
@@ -519,13 +531,16 @@ def _backward(plan: StackPlan, graph, tape, packed, head, g_logits, g_outs, need
         extra.setdefault(plan.outputs[0], []).append(planes_linear_bwd_input(glp, head[0], head[0].shape[1]))
         tape.emb_planes = None
     dX = {}             # layer index -> fp32 [N, k] gradient of its concatenated (dropped) input
+    masked = set()      # layers whose dX already includes their own feat_drop mask
     for i in range(nL - 1, -1, -1):
         L = plan.layers[i]
         conv = L.conv
         srcs = []
         for ci, off in plan.consumers.get(L.output, []):
             if ci in dX and dX[ci] is not None and off < dX[ci].shape[1]:
-                srcs.append((dX[ci], off, tape.pdrop[ci], tape.fseed[ci], (plan.layers[ci].k_in + 3) // 4))
+                # a dX that came out of the masked dX GEMM below already carries layer ci's feat_drop mask
+                pm = 0.0 if ci in masked else tape.pdrop[ci]
+                srcs.append((dX[ci], off, pm, tape.fseed[ci], (plan.layers[ci].k_in + 3) // 4))
         for g in extra.get(L.output, []):
             srcs.append((g, 0, 0.0, 0, 1))
         if not srcs:
@@ -587,7 +602,12 @@ def _backward(plan: StackPlan, graph, tape, packed, head, g_logits, g_outs, need
         for t, off in zip(L.inputs, L.in_offs):
             if t in plan.producer:
                 k_need = off + plan.widths[t]
-        dX[i] = planes_linear_bwd_input(dY, packed[i], k_need) if k_need else None
+        if FOLD_MASK:
+            dX[i] = planes_linear_bwd_input(dY, packed[i], k_need, drop_p=tape.pdrop[i], seed=tape.fseed[i],
+                                            concat_chunks=(L.k_in + 3) // 4) if k_need else None
+            masked.add(i)
+        else:
+            dX[i] = planes_linear_bwd_input(dY, packed[i], k_need) if k_need else None
         del dY, Y, att, ins
     return d_packed, d_bias, d_hw, d_hb
 

@@ -807,3 +807,26 @@ def test_distance_pe_tree_kernel_equals_all_pairs_kernel_and_oracle(mods, monkey
             continue
         ref, _, diam = mods["ope"].dist_pos_enc(a, anchors[i].cpu().tolist())
         assert int(d_fast[i]) == diam and np.array_equal(pe_fast[off[i]:off[i + 1]].cpu().numpy(), ref), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,k_off,cc", [(1000, 260, 384, 0, 0), (333, 516, 768, 0, 192), (257, 130, 132, 64, 70)])
+def test_dx_gemm_with_the_consumer_dropout_mask_in_its_epilogue(mods, M, N, K, k_off, cc):
+    """spgnn_planes_linear_bwd_input_masked == unmasked dX times the feat_drop mask every plane producer derives from
+    (seed, row, 4-column chunk) — the mask split_planes applies in the forward (GATConv's feat_drop, models.py:301-314
+    via DGL GATConv.forward): the producing layer's backward then reads a finished gradient."""
+    from spgnn_b200 import stack
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    dC = stack.split_planes(torch.randn(M, N, device=dev))
+    W = torch.randn(N, k_off + K, device=dev)
+    p, seed = 0.1, 4242
+    plain = stack.planes_linear_bwd_input(dC, W, K, k_off=k_off)
+    masked = stack.planes_linear_bwd_input(dC, W, K, k_off=k_off, drop_p=p, seed=seed, concat_chunks=cc)
+    nch = cc if cc > 0 else (k_off + K + 3) // 4
+    keep = stack.split_planes(torch.ones(M, K, device=dev), p=p, seed=seed, concat_chunks=nch, chunk_off=k_off // 4).float()
+    frac = float((keep == 0).float().mean())
+    assert 0.07 < frac < 0.13
+    assert torch.equal(masked[:, :K], plain[:, :K] * keep)
+    again = stack.planes_linear_bwd_input(dC, W, K, k_off=k_off, drop_p=p, seed=seed + 1, concat_chunks=cc)
+    assert not torch.equal(again[:, :K], masked[:, :K])
