@@ -79,6 +79,68 @@ struct NtShared {
     uint32_t tmem_base;
 };
 
+// Epilogue of one 128 x BN accumulator for one warp (TMEM lanes 32 * warp ..): TMEM -> registers -> padded smem staging
+// tile -> global, so that every store instruction writes whole 128-byte row segments.
+__device__ __forceinline__ void nt_epilogue_tile(const NtArgs& g, uint32_t stg, uint32_t taddr, int64_t m0, int n0,
+                                                 int ncols, int warp, int lane, bool vec_ok, bool plain) {
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            st_shared4(stg + (lane * kStgLd + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int cc = (lane & 7) * 4;
+        const int col = n0 + c0 + cc;
+        const int rsub = lane >> 3;                                   // row within each group of 4
+        const int64_t row0 = m0 + warp * 32 + rsub;
+        float* q = g.C + row0 * g.ldc + col;
+        const int64_t qstep = 4 * g.ldc;
+        const int nrow = (int)max((int64_t)0, min((int64_t)8, (g.M - row0 + 3) / 4));
+        const uint32_t sp = stg + (rsub * kStgLd + cc) * 4;
+        if (plain && vec_ok && c0 + 32 <= ncols) {
+            if (g.mthr) {
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr)
+                    if (itr < nrow)
+                        st4(q + itr * qstep, nt_mask4(g, ld_shared4(sp + itr * (4 * kStgLd * 4)), row0 + 4 * itr, col));
+            } else {
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr)
+                    if (itr < nrow) st4(q + itr * qstep, ld_shared4(sp + itr * (4 * kStgLd * 4)));
+            }
+        } else {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias) {
+                if (col + 0 < g.N) bv.x = __ldg(g.bias + col + 0);
+                if (col + 1 < g.N) bv.y = __ldg(g.bias + col + 1);
+                if (col + 2 < g.N) bv.z = __ldg(g.bias + col + 2);
+                if (col + 3 < g.N) bv.w = __ldg(g.bias + col + 3);
+            }
+            const int nvalid = ncols - (c0 + cc);
+            for (int itr = 0; itr < nrow; ++itr) {
+                float4 x = ld_shared4(sp + itr * (4 * kStgLd * 4));
+                x.x = act_fwd(x.x + bv.x, g.act, g.slope);
+                x.y = act_fwd(x.y + bv.y, g.act, g.slope);
+                x.z = act_fwd(x.z + bv.z, g.act, g.slope);
+                x.w = act_fwd(x.w + bv.w, g.act, g.slope);
+                if (g.mthr) x = nt_mask4(g, x, row0 + 4 * itr, col);
+                float* qq = q + itr * qstep;
+                if (vec_ok && nvalid >= 4) st4(qq, x);
+                else {
+                    if (nvalid > 0) qq[0] = x.x;
+                    if (nvalid > 1) qq[1] = x.y;
+                    if (nvalid > 2) qq[2] = x.z;
+                    if (nvalid > 3) qq[3] = x.w;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // CL = 2: clusters of two CTAs work on two adjacent m-tiles of the SAME n-tile in lock step; each CTA fetches half of
 // the weight tile and multicasts it to both, so the B tile crosses the L2 -> SM fabric once per cluster.  The ncu
 // capture of the CL = 1 kernel (profiles/r01_ncu_full_step_79ms_*) shows the big projections bound by that fabric
@@ -138,62 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
             mbar_wait(smem_u32(&sh->tmem_full[buf]), par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kMaxBN);
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    st_shared4(stg + (lane * kStgLd + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-                const int cc = (lane & 7) * 4;
-                const int col = n0 + c0 + cc;
-                const int rsub = lane >> 3;                                   // row within each group of 4
-                const int64_t row0 = m0 + warp * 32 + rsub;
-                float* q = g.C + row0 * g.ldc + col;
-                const int64_t qstep = 4 * g.ldc;
-                const int nrow = (int)max((int64_t)0, min((int64_t)8, (g.M - row0 + 3) / 4));
-                const uint32_t sp = stg + (rsub * kStgLd + cc) * 4;
-                if (plain && vec_ok && c0 + 32 <= ncols) {
-                    if (g.mthr) {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nrow)
-                                st4(q + itr * qstep, nt_mask4(g, ld_shared4(sp + itr * (4 * kStgLd * 4)), row0 + 4 * itr, col));
-                    } else {
-#pragma unroll
-                        for (int itr = 0; itr < 8; ++itr)
-                            if (itr < nrow) st4(q + itr * qstep, ld_shared4(sp + itr * (4 * kStgLd * 4)));
-                    }
-                } else {
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (g.bias) {
-                        if (col + 0 < g.N) bv.x = __ldg(g.bias + col + 0);
-                        if (col + 1 < g.N) bv.y = __ldg(g.bias + col + 1);
-                        if (col + 2 < g.N) bv.z = __ldg(g.bias + col + 2);
-                        if (col + 3 < g.N) bv.w = __ldg(g.bias + col + 3);
-                    }
-                    const int nvalid = ncols - (c0 + cc);
-                    for (int itr = 0; itr < nrow; ++itr) {
-                        float4 x = ld_shared4(sp + itr * (4 * kStgLd * 4));
-                        x.x = act_fwd(x.x + bv.x, g.act, g.slope);
-                        x.y = act_fwd(x.y + bv.y, g.act, g.slope);
-                        x.z = act_fwd(x.z + bv.z, g.act, g.slope);
-                        x.w = act_fwd(x.w + bv.w, g.act, g.slope);
-                        if (g.mthr) x = nt_mask4(g, x, row0 + 4 * itr, col);
-                        float* qq = q + itr * qstep;
-                        if (vec_ok && nvalid >= 4) st4(qq, x);
-                        else {
-                            if (nvalid > 0) qq[0] = x.x;
-                            if (nvalid > 1) qq[1] = x.y;
-                            if (nvalid > 2) qq[2] = x.z;
-                            if (nvalid > 3) qq[3] = x.w;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            nt_epilogue_tile(g, stg, taddr, m0, n0, ncols, warp, lane, vec_ok, plain);
             tc_fence_before();
             mbar_arrive(smem_u32(&sh->tmem_empty[buf]));
         }
@@ -273,6 +280,138 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
     if (warp == kEpiWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- NT, CTA pairs
+// The same GEMM with tcgen05 cta_group::2: a cluster of two CTAs (the two SMs of a TPC) owns a 256 x BN tile.  Each
+// CTA loads ITS 128 rows of A and HALF of the weight tile (BN / 2 rows), the leader issues one M = 256 UMMA per
+// (k-step, pass) that reads both halves, and each CTA drains its own 128 accumulator lanes.  Per CTA and k-block that
+// is 32 KB + BN * 128 B through the L2 -> SM path instead of 32 KB + BN * 256 B: the chip-wide L2 throughput
+// (~6300 B/clk = 42.6 B/clk/SM) is what bounds the single-CTA kernel on the big projections (tensor pipe 62 - 73 %),
+// and TMA multicast does not relieve it at cluster size 2 (nt_planes_kernel<2>, measured neutral).
+// Barriers: full[s] of the LEADER collects the transaction bytes of both CTAs' loads (cp.async.bulk.tensor
+// .cta_group::2 signals the peer's barrier); empty[s] / tmem_full[b] are arrived in both CTAs by multicast commits;
+// tmem_empty[b] of the leader counts the epilogue threads of both CTAs (the peer arrives through the cluster window).
+__global__ void __launch_bounds__(kThreads, 1) nt_pair_kernel(const __grid_constant__ NtMaps maps, const NtArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stages_bytes = g.stages * g.stage_bytes;
+    NtShared* sh = reinterpret_cast<NtShared*>(smem + stages_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(smem_u32(&sh->full[s]), 1);          // leader: its producer's arrive.expect_tx (bytes of both CTAs)
+            mbar_init(smem_u32(&sh->empty[s]), 1);         // multicast commit of the leader's UMMA issuer
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&sh->tmem_full[b]), 1);     // multicast commit
+            mbar_init(smem_u32(&sh->tmem_empty[b]), 2 * kEpiWarps * 32);   // leader: epilogue threads of both CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 5 && lane == 0) {
+        prefetch_tmap(&maps.a1);
+        if (g.kb2 > 0) prefetch_tmap(&maps.a2);
+        prefetch_tmap(&maps.b);
+    }
+    if (warp == kEpiWarps) tmem_alloc_pair(smem_u32(&sh->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // both CTAs' barriers and TMEM exist before anything crosses the pair
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    const int64_t n_tiles = ((g.nt_m + 1) / 2) * g.nt_n;
+    const int64_t tile0 = blockIdx.x / 2, tile_step = gridDim.x / 2;
+    const int nkb = g.kb1 + g.kb2;
+    const int half = g.BN / 2;               // weight rows held by each CTA
+
+    if (warp < kEpiWarps) {
+        // ===================================================== epilogue (both CTAs, own accumulator lanes)
+        int it = 0;
+        const uint32_t stg = smem_base + stages_bytes + 256 + warp * (32 * kStgLd * 4);
+        const bool vec_ok = (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+        const bool plain = (g.act == SPGNN_ACT_NONE) && (g.bias == nullptr);
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+            const int buf = it & 1;
+            const uint32_t par = (it >> 1) & 1;
+            const int64_t m0 = ((tile / g.nt_n) * 2 + rank) * BM;
+            const int n0 = (int)(tile % g.nt_n) * g.BN;
+            const int ncols = min(g.BN, g.N - n0);
+            mbar_wait(smem_u32(&sh->tmem_full[buf]), par);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kMaxBN);
+            nt_epilogue_tile(g, stg, taddr, m0, n0, ncols, warp, lane, vec_ok, plain);
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_u32(smem_u32(&sh->tmem_empty[buf]), 0));
+        }
+    } else if (warp == kEpiWarps) {
+        // ===================================================== UMMA issuer (leader CTA, one elected thread)
+        if (leader && lane == 0) {
+            int it = 0;
+            uint32_t kcount = 0;
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+                const int buf = it & 1;
+                const uint32_t par = (it >> 1) & 1;
+                const uint32_t idesc = make_idesc_pair(g.BN);
+                mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);     // both epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kMaxBN);
+                for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                    const int s = kcount % g.stages;
+                    const uint32_t sp = (kcount / g.stages) & 1;
+                    mbar_wait(smem_u32(&sh->full[s]), sp);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_base + s * g.stage_bytes;
+                    const uint32_t a_lo = a_hi + BM * 128;
+                    const uint32_t b_hi = a_hi + kABytes;
+                    const uint32_t b_lo = b_hi + half * 128;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t ko = k * 32;
+                        const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                        const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                        umma_bf16_pair(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                        umma_bf16_pair(tmem_d, dah, dbl, idesc, 1);
+                        umma_bf16_pair(tmem_d, dal, dbh, idesc, 1);
+                    }
+                    umma_commit_pair(smem_u32(&sh->empty[s]), 3);       // the stage is free in both CTAs
+                }
+                umma_commit_pair(smem_u32(&sh->tmem_full[buf]), 3);     // accumulators complete -> both epilogues
+            }
+        }
+    } else if (lane == 0) {
+        // ===================================================== TMA producer (one thread per CTA)
+        uint32_t kcount = 0;
+        const uint32_t tx = 2u * (uint32_t)g.stage_bytes;               // both CTAs' loads land on the leader's barrier
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            const int m0 = (int)(((tile / g.nt_n) * 2 + rank) * BM);
+            const int n0 = (int)(tile % g.nt_n) * g.BN + (int)rank * half;
+            for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                const int s = kcount % g.stages;
+                const uint32_t sp = (kcount / g.stages) & 1;
+                mbar_wait(smem_u32(&sh->empty[s]), sp ^ 1);
+                const uint32_t bar = mapa_u32(smem_u32(&sh->full[s]), 0);
+                if (leader) mbar_expect_tx(smem_u32(&sh->full[s]), tx);
+                const uint32_t dst = smem_base + s * g.stage_bytes;
+                if (kb < g.kb1) tma_load_3d_pair(dst, &maps.a1, bar, kb * BK, m0, 0);
+                else tma_load_3d_pair(dst, &maps.a2, bar, (kb - g.kb1) * BK, m0, 0);
+                tma_load_3d_pair(dst + kABytes, &maps.b, bar, kb * BK, n0, 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // no CTA leaves (or frees TMEM) while its peer may still use the pair
+    if (warp == kEpiWarps) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
@@ -583,6 +722,144 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
     if (warp == kWideEpiWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// The wide kernel on CTA pairs (see nt_pair_kernel): a pair owns 256 rows x BN columns x H heads; each CTA loads its A
+// tile and HALF of every weight tile (48 instead of 64 KB per k-block at BN = 128).  Opt-in: measured slower than the
+// single-CTA kernel at the bench size (see spgnn_wide_linear).
+__global__ void __launch_bounds__(kWideThreads, 1) wide_pair_kernel(const __grid_constant__ WideMaps maps, const WideArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stages_bytes = g.stages * g.stage_bytes;
+    NtShared* sh = reinterpret_cast<NtShared*>(smem + stages_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(smem_u32(&sh->full[s]), 1);
+            mbar_init(smem_u32(&sh->empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&sh->tmem_full[b]), 1);
+            mbar_init(smem_u32(&sh->tmem_empty[b]), 2 * kWideEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kWideEpiWarps + 1 && lane == 0) {
+        prefetch_tmap(&maps.a);
+        prefetch_tmap(&maps.b);
+    }
+    if (warp == kWideEpiWarps) tmem_alloc_pair(smem_u32(&sh->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    const int64_t n_tiles = ((g.nt_m + 1) / 2) * g.nt_n;
+    const int64_t tile0 = blockIdx.x / 2, tile_step = gridDim.x / 2;
+    const int nkb = g.nparts * g.kbp;                // k-blocks per head
+    const int accw = g.H * g.BN;                     // TMEM columns per accumulator buffer
+    const int half = g.BN / 2;
+
+    if (warp < kWideEpiWarps) {
+        // ===================================================== epilogue (both CTAs)
+        int it = 0;
+        const uint32_t stg = smem_base + stages_bytes + 256 + warp * (32 * 16 * 4);
+        float* dbias_row = g.dbias_ws ? g.dbias_ws + (int64_t)blockIdx.x * (g.H * g.F) : nullptr;
+        const uint32_t empty_leader0 = mapa_u32(smem_u32(&sh->tmem_empty[0]), 0);
+        const uint32_t empty_leader1 = mapa_u32(smem_u32(&sh->tmem_empty[1]), 0);
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+            const int buf = it & 1;
+            const uint32_t par = (it >> 1) & 1;
+            const int64_t m0 = ((tile / g.nt_n) * 2 + rank) * BM;
+            const int n0 = (int)(tile % g.nt_n) * g.BN;
+            const int ncols = min(g.BN, g.F - n0);
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * accw);
+            const uint32_t fb = smem_u32(&sh->tmem_full[buf]);
+            if (g.mode == 0) {
+                if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU, 0>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE, 0>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else wide_epilogue_tile<-1, 0>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+            } else {
+                if (g.act == SPGNN_ACT_ELU) wide_epilogue_tile<SPGNN_ACT_ELU, 1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else if (g.act == SPGNN_ACT_NONE) wide_epilogue_tile<SPGNN_ACT_NONE, 1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+                else wide_epilogue_tile<-1, 1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(buf ? empty_leader1 : empty_leader0);
+        }
+    } else if (warp == kWideEpiWarps) {
+        // ===================================================== UMMA issuer (leader, one thread)
+        if (leader && lane == 0) {
+            int it = 0;
+            uint32_t kcount = 0;
+            const uint32_t idesc = make_idesc_pair(g.BN);
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+                const int buf = it & 1;
+                const uint32_t par = (it >> 1) & 1;
+                mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);
+                tc_fence_after();
+                for (int h = 0; h < g.H; ++h) {
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * accw + h * g.BN);
+                    for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                        const int s = kcount % g.stages;
+                        const uint32_t sp = (kcount / g.stages) & 1;
+                        mbar_wait(smem_u32(&sh->full[s]), sp);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_base + s * g.stage_bytes;
+                        const uint32_t a_lo = a_hi + BM * 128;
+                        const uint32_t b_hi = a_hi + kABytes;
+                        const uint32_t b_lo = b_hi + half * 128;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t ko = k * 32;
+                            const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                            const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                            umma_bf16_pair(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                            umma_bf16_pair(tmem_d, dah, dbl, idesc, 1);
+                            umma_bf16_pair(tmem_d, dal, dbh, idesc, 1);
+                        }
+                        umma_commit_pair(smem_u32(&sh->empty[s]), 3);
+                    }
+                }
+                umma_commit_pair(smem_u32(&sh->tmem_full[buf]), 3);
+            }
+        }
+    } else if (lane == 0) {
+        // ===================================================== TMA producer (one thread per CTA)
+        uint32_t kcount = 0;
+        const uint32_t tx = 2u * (uint32_t)g.stage_bytes;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            const int m0 = (int)(((tile / g.nt_n) * 2 + rank) * BM);
+            const int n0 = (int)(tile % g.nt_n) * g.BN + (int)rank * half;
+            for (int h = 0; h < g.H; ++h) {
+                for (int kb = 0; kb < nkb; ++kb, ++kcount) {
+                    const int s = kcount % g.stages;
+                    const uint32_t sp = (kcount / g.stages) & 1;
+                    mbar_wait(smem_u32(&sh->empty[s]), sp ^ 1);
+                    const uint32_t bar = mapa_u32(smem_u32(&sh->full[s]), 0);
+                    if (leader) mbar_expect_tx(smem_u32(&sh->full[s]), tx);
+                    const uint32_t dst = smem_base + s * g.stage_bytes;
+                    const int part = kb / g.kbp, j = kb - part * g.kbp;
+                    const int acol = (part == 0 ? h : g.H) * g.kp + j * BK;
+                    tma_load_3d_pair(dst, &maps.a, bar, acol, m0, 0);
+                    tma_load_3d_pair(dst + kABytes, &maps.b, bar, kb * BK, h * g.F + n0, 0);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == kWideEpiWarps) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
@@ -943,6 +1220,60 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
     NtMaps maps;
     NtArgs a{};
     pick_bn((int)N, &a.BN, &a.nt_n);
+    // CTA pairs (cta_group::2) unless SPGNN_NT_PAIR=0
+    static int pair_clusters = -1;
+    if (pair_clusters < 0) {
+        pair_clusters = 0;
+        const char* e = getenv("SPGNN_NT_PAIR");
+        if (!e || atoi(e) != 0) {
+            SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = kSmemLimit; cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, nt_pair_kernel, &cfg) == cudaSuccess) pair_clusters = n;
+            else (void)cudaGetLastError();
+        }
+    }
+    // Measured on 1.23 M rows (profiles/r02_nt_pair_vs_single.txt): gat0 / gat1 forward -12 % / -19 %, dX of gat1 /
+    // gat2 / the output layer -17 % / -16 % / -28 %; output-bound shapes (small K: pgnn0-2, K = 192 -> 4100 columns)
+    // lose 10 - 30 % to the coupling of the two epilogues, so they stay on the single-CTA kernel
+    if (pair_clusters > 0 && K1 + K2 >= 256 && N >= 320 && ceil_div(M, BM) >= 4 * (int64_t)pair_clusters) {
+        int rc = make_planes_map(&maps.a1, A1, M, K1, lda1, ps1, BK, BM);
+        if (rc) return rc;
+        if (A2 && K2 > 0) {
+            rc = make_planes_map(&maps.a2, A2, M, K2, lda2, ps2, BK, BM);
+            if (rc) return rc;
+        } else {
+            maps.a2 = maps.a1;
+        }
+        rc = make_planes_map(&maps.b, Bhi, N, ldb, ldb, N * ldb, BK, a.BN / 2);
+        if (rc) return rc;
+        a.bias = bias; a.act = act; a.slope = slope; a.C = C; a.ldc = ldc; a.M = M; a.N = (int)N;
+        a.mthr = mask_p > 0.f ? (uint32_t)(mask_p * 65536.f + 0.5f) : 0u;
+        a.mscale = mask_p > 0.f ? 1.f / (1.f - mask_p) : 1.f;
+        a.mseed = mask_seed; a.mnch = mask_chunks > 0 ? mask_chunks : (N + 3) / 4; a.moff = mask_chunk_off;
+        a.nt_m = ceil_div(M, BM);
+        a.kb1 = (int)ceil_div(K1, BK);
+        a.kb2 = (A2 && K2 > 0) ? (int)ceil_div(K2, BK) : 0;
+        a.stage_bytes = kABytes + a.BN * 128;           // this CTA's A tile + its half of the weight tile
+        a.stages = (kSmemLimit - kNtFixed) / a.stage_bytes;
+        if (a.stages > kMaxStages) a.stages = kMaxStages;
+        const int64_t items = ceil_div(a.nt_m, 2) * a.nt_n;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)(2 * (items < pair_clusters ? items : pair_clusters)));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemLimit; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        SPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, nt_pair_kernel, maps, a));
+        count_launch();
+        return SPGNN_OK;
+    }
     // clusters pay when several m-tiles share a weight tile that is worth a k-loop: not for skinny outputs
     const bool cluster = max_clusters > 0 && ceil_div(M, BM) >= 4 * (int64_t)max_clusters && a.BN >= 64;
     int rc = make_planes_map(&maps.a1, A1, M, K1, lda1, ps1, BK, BM);
@@ -1106,21 +1437,59 @@ extern "C" int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa,
     if (rc) return rc;
     rc = make_planes_map(&maps.b, hi, HF, ldb, ldb, HF * ldb, BK, a.BN);
     if (rc) return rc;
-    a.stage_bytes = kABytes + a.BN * 256;
+    // CTA pairs (cta_group::2) are OPT-IN here (SPGNN_WIDE_PAIR=1): correct (scripts/wide_pair_probe.py), but slower at
+    // the bench size -- forward 5.71 -> 6.05 ms, backward 6.52 -> 7.54 ms (profiles/r02_wide_pair_probe.txt): with
+    // BN = 128 and a 16-warp epilogue per CTA the leader's wait for BOTH epilogues costs more than the halved weight
+    // traffic saves.  Needs F % BN == 0 (every CTA loads exactly half a weight tile) and enough m-tiles for every pair
+    static int pair_clusters = -1;
+    if (pair_clusters < 0) {
+        pair_clusters = 0;
+        const char* e = getenv("SPGNN_WIDE_PAIR");
+        if (e && atoi(e) == 1) {
+            SPGNN_CUDA_OK(cudaFuncSetAttribute(wide_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(kWideThreads);
+            cfg.dynamicSmemBytes = kSmemLimit; cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, wide_pair_kernel, &cfg) == cudaSuccess) pair_clusters = n;
+            else (void)cudaGetLastError();
+        }
+    }
+    const bool pair = pair_clusters > 0 && F % a.BN == 0 && a.BN % 32 == 0 && a.nt_m >= 4 * (int64_t)pair_clusters;
+    if (pair) {
+        rc = make_planes_map(&maps.b, hi, HF, ldb, ldb, HF * ldb, BK, a.BN / 2);
+        if (rc) return rc;
+    }
+    a.stage_bytes = kABytes + a.BN * (pair ? 128 : 256);
     const int fixed = kWideFixed;
     a.stages = (kSmemLimit - fixed) / a.stage_bytes;
     if (a.stages > kMaxStages) a.stages = kMaxStages;
     SPGNN_REQUIRE(a.stages >= 2, "wide_linear: not enough shared memory for two pipeline stages");
-    const int64_t tiles = a.nt_m * a.nt_n;
-    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    const int64_t tiles = pair ? ceil_div(a.nt_m, 2) * a.nt_n : a.nt_m * a.nt_n;
+    const unsigned grid = pair ? (unsigned)(2 * (tiles < pair_clusters ? tiles : pair_clusters))
+                               : (unsigned)(tiles < sm_count() ? tiles : sm_count());
     float* part = nullptr;
     if (mode == 1 && dbias) {
         part = reinterpret_cast<float*>(((uintptr_t)(hi + 2 * HF * ldb) + 255) & ~(uintptr_t)255);
         a.dbias_ws = part;
         SPGNN_CUDA_OK(cudaMemsetAsync(part, 0, (size_t)grid * HF * sizeof(float), st));
     }
-    wide_kernel<<<grid, kWideThreads, kSmemLimit, st>>>(maps, a);
-    SPGNN_LAUNCH_OK();
+    if (pair) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kWideThreads);
+        cfg.dynamicSmemBytes = kSmemLimit; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        SPGNN_CUDA_OK(cudaLaunchKernelEx(&cfg, wide_pair_kernel, maps, a));
+        count_launch();
+    } else {
+        wide_kernel<<<grid, kWideThreads, kSmemLimit, st>>>(maps, a);
+        SPGNN_LAUNCH_OK();
+    }
     if (part) {
         wide_dbias_reduce_kernel<<<(unsigned)ceil_div(HF, 128), 128, 0, st>>>(part, grid, HF, dbias);
         SPGNN_LAUNCH_OK();

@@ -128,6 +128,56 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int n, bool mn_major) {
     return d;
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE UMMA of M = 256; each CTA holds
+// its 128 rows of A, HALF of the B tile (N / 2 rows) and its 128 lanes of the accumulator; the leader (rank 0) issues.
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of any CTA of the cluster (cluster-window address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA tile load into THIS CTA's shared memory, completion bytes signalled on an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// both CTAs of the pair call these with the same warp and the same destination offset
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this CTA-relative address in every CTA of cta_mask once the pair's UMMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+// instruction descriptor of the pair UMMA: M = 256 (128 per CTA), N = the whole tile width
+__host__ __device__ __forceinline__ uint32_t make_idesc_pair(int n) {
+    uint32_t d = (1u << 4) | (1u << 7) | (1u << 10);
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(256 >> 4) << 24;
+    return d;
+}
+
 // fp32 pair -> packed bf16 (hi) and packed bf16 of the remainders (lo); low half = first element.
 // a = hi + lo + r with |r| <= 2^-18 |a|.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {

@@ -827,6 +827,7 @@ def test_dx_gemm_with_the_consumer_dropout_mask_in_its_epilogue(mods, M, N, K, k
     keep = stack.split_planes(torch.ones(M, K, device=dev), p=p, seed=seed, concat_chunks=nch, chunk_off=k_off // 4).float()
     frac = float((keep == 0).float().mean())
     assert 0.07 < frac < 0.13
-    assert torch.equal(masked[:, :K], plain[:, :K] * keep)
+    scale = torch.tensor(1.0, device=dev) / (torch.tensor(1.0, device=dev) - torch.tensor(p, device=dev))   # fp32, as the kernel
+    assert torch.equal(masked[:, :K], torch.where(keep != 0, plain[:, :K] * scale, torch.zeros_like(plain[:, :K])))
     again = stack.planes_linear_bwd_input(dC, W, K, k_off=k_off, drop_p=p, seed=seed + 1, concat_chunks=cc)
     assert not torch.equal(again[:, :K], masked[:, :K])
