@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_pair_kernel(const __grid_const
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&sh->tmem_full[b]), 1);     // multicast commit
-            mbar_init(smem_u32(&sh->tmem_empty[b]), 2 * kEpiWarps * 32);   // leader: epilogue threads of both CTAs
+            mbar_init(smem_u32(&sh->tmem_empty[b]), 2 * kEpiWarps);        // leader: one arrival per epilogue warp of both CTAs
         }
         fence_barrier_init();
     }
@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) nt_pair_kernel(const __grid_const
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kMaxBN);
             nt_epilogue_tile(g, stg, taddr, m0, n0, ncols, warp, lane, vec_ok, plain);
             tc_fence_before();
-            mbar_arrive_cluster(mapa_u32(smem_u32(&sh->tmem_empty[buf]), 0));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sh->tmem_empty[buf]), 0));
         }
     } else if (warp == kEpiWarps) {
         // ===================================================== UMMA issuer (leader CTA, one elected thread)
@@ -745,7 +746,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_pair_kernel(const __grid
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&sh->tmem_full[b]), 1);
-            mbar_init(smem_u32(&sh->tmem_empty[b]), 2 * kWideEpiWarps * 32);
+            mbar_init(smem_u32(&sh->tmem_empty[b]), 2 * kWideEpiWarps);
         }
         fence_barrier_init();
     }
@@ -791,7 +792,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_pair_kernel(const __grid
                 else wide_epilogue_tile<-1, 1>(g, stg, dbias_row, taddr, m0, n0, ncols, warp, lane, fb, par);
             }
             tc_fence_before();
-            mbar_arrive_cluster(buf ? empty_leader1 : empty_leader0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf ? empty_leader1 : empty_leader0);
         }
     } else if (warp == kWideEpiWarps) {
         // ===================================================== UMMA issuer (leader, one thread)
@@ -1238,10 +1240,12 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
             else (void)cudaGetLastError();
         }
     }
-    // Measured on 1.23 M rows (profiles/r02_nt_pair_vs_single.txt): gat0 / gat1 forward -12 % / -19 %, dX of gat1 /
-    // gat2 / the output layer -17 % / -16 % / -28 %; output-bound shapes (small K: pgnn0-2, K = 192 -> 4100 columns)
-    // lose 10 - 30 % to the coupling of the two epilogues, so they stay on the single-CTA kernel
-    if (pair_clusters > 0 && K1 + K2 >= 256 && N >= 320 && ceil_div(M, BM) >= 4 * (int64_t)pair_clusters) {
+    // Measured on 1.23 M rows (profiles/r02_nt_pair_vs_single.txt): gat0 / gat1 forward -6..-12 % / -19..-25 %, dX of
+    // gat1 / the output layer (K = 4100 -> 192 columns) -17..-21 % / -28 %; output-bound shapes (small K: pgnn0-2,
+    // K = 192 -> 4100 columns) lose 10 - 30 % to the coupling of the two epilogues and stay on the single-CTA kernel
+    const int64_t Kt = K1 + K2;
+    if (pair_clusters > 0 && Kt >= 256 && (N >= 320 || Kt >= 512) && N >= 64 &&
+        ceil_div(M, BM) >= 4 * (int64_t)pair_clusters) {
         int rc = make_planes_map(&maps.a1, A1, M, K1, lda1, ps1, BK, BM);
         if (rc) return rc;
         if (A2 && K2 > 0) {
