@@ -205,10 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
             mbar_arrive(smem_u32(&sh->tmem_empty[buf]));
         }
     } else if (warp == kEpiWarps) {
-        // ===================================================== UMMA issuer (one elected thread)
-        if (lane == 0) {
+        // ===================================================== UMMA issuer: the whole warp walks the loop, one elected
+        // lane issues (see nt_pair_kernel: `if (lane == 0)` around the loop costs an ELECT / R2UR waterfall per UMMA)
+        {
             int it = 0;
             uint32_t kcount = 0;
+            const uint32_t tbase = __shfl_sync(kFull, tmem_base, 0);
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
                 const int buf = it & 1;
                 const uint32_t par = (it >> 1) & 1;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                 const uint32_t idesc = make_idesc(n_mma, false);
                 mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);     // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kMaxBN);
+                const uint32_t tmem_d = tbase + (uint32_t)(buf * kMaxBN);
                 for (int kb = 0; kb < nkb; ++kb, ++kcount) {
                     const int s = kcount % g.stages;
                     const uint32_t sp = (kcount / g.stages) & 1;
@@ -228,20 +230,24 @@ __global__ void __launch_bounds__(kThreads, 1) nt_planes_kernel(const __grid_con
                     const uint32_t a_lo = a_hi + BM * 128;
                     const uint32_t b_hi = a_hi + kABytes;
                     const uint32_t b_lo = b_hi + g.BN * 128;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t ko = k * 32;      // 16 bf16 = 32 bytes along the swizzled row
-                        const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
-                        const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
-                        umma_bf16(tmem_d, dah, dbh, idesc, (kb | k) != 0);
-                        umma_bf16(tmem_d, dah, dbl, idesc, 1);
-                        umma_bf16(tmem_d, dal, dbh, idesc, 1);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t ko = k * 32;      // 16 bf16 = 32 bytes along the swizzled row
+                            const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                            const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                            umma_bf16(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                            umma_bf16(tmem_d, dah, dbl, idesc, 1);
+                            umma_bf16(tmem_d, dal, dbh, idesc, 1);
+                        }
+                        // frees the smem stage when these UMMAs retire (in both CTAs of a cluster)
+                        if (CL > 1) umma_commit_mc(smem_u32(&sh->empty[s]), (uint16_t)((1u << CL) - 1));
+                        else umma_commit(smem_u32(&sh->empty[s]));
                     }
-                    // frees the smem stage when these UMMAs retire (in both CTAs of a cluster)
-                    if (CL > 1) umma_commit_mc(smem_u32(&sh->empty[s]), (uint16_t)((1u << CL) - 1));
-                    else umma_commit(smem_u32(&sh->empty[s]));
+                    __syncwarp();
                 }
-                umma_commit(smem_u32(&sh->tmem_full[buf]));    // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(smem_u32(&sh->tmem_full[buf]));    // accumulator complete -> epilogue
+                __syncwarp();
             }
         }
     } else if (lane == 0) {
@@ -352,17 +358,22 @@ __global__ void __launch_bounds__(kThreads, 1) nt_pair_kernel(const __grid_const
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sh->tmem_empty[buf]), 0));
         }
     } else if (warp == kEpiWarps) {
-        // ===================================================== UMMA issuer (leader CTA, one elected thread)
-        if (leader && lane == 0) {
+        // ===================================================== UMMA issuer (leader CTA)
+        // The WHOLE warp walks the loop and one elected lane issues: inside `if (lane == 0)` the operands of every
+        // UMMA (descriptors, TMEM address, instruction descriptor) live in vector registers of a divergent thread and
+        // ptxas wraps each tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~16 instructions, ~110
+        // cycles per UMMA for the single issuing thread -- more than an N = 128 UMMA takes to execute).
+        if (leader) {
             int it = 0;
             uint32_t kcount = 0;
+            const uint32_t idesc = make_idesc_pair(g.BN);
+            const uint32_t tbase = __shfl_sync(kFull, tmem_base, 0);
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
                 const int buf = it & 1;
                 const uint32_t par = (it >> 1) & 1;
-                const uint32_t idesc = make_idesc_pair(g.BN);
                 mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);     // both epilogues drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kMaxBN);
+                const uint32_t tmem_d = tbase + (uint32_t)(buf * kMaxBN);
                 for (int kb = 0; kb < nkb; ++kb, ++kcount) {
                     const int s = kcount % g.stages;
                     const uint32_t sp = (kcount / g.stages) & 1;
@@ -372,18 +383,22 @@ __global__ void __launch_bounds__(kThreads, 1) nt_pair_kernel(const __grid_const
                     const uint32_t a_lo = a_hi + BM * 128;
                     const uint32_t b_hi = a_hi + kABytes;
                     const uint32_t b_lo = b_hi + half * 128;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t ko = k * 32;
-                        const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
-                        const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
-                        umma_bf16_pair(tmem_d, dah, dbh, idesc, (kb | k) != 0);
-                        umma_bf16_pair(tmem_d, dah, dbl, idesc, 1);
-                        umma_bf16_pair(tmem_d, dal, dbh, idesc, 1);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t ko = k * 32;
+                            const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                            const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                            umma_bf16_pair(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                            umma_bf16_pair(tmem_d, dah, dbl, idesc, 1);
+                            umma_bf16_pair(tmem_d, dal, dbh, idesc, 1);
+                        }
+                        umma_commit_pair(smem_u32(&sh->empty[s]), 3);       // the stage is free in both CTAs
                     }
-                    umma_commit_pair(smem_u32(&sh->empty[s]), 3);       // the stage is free in both CTAs
+                    __syncwarp();
                 }
-                umma_commit_pair(smem_u32(&sh->tmem_full[buf]), 3);     // accumulators complete -> both epilogues
+                if (elect_one()) umma_commit_pair(smem_u32(&sh->tmem_full[buf]), 3);   // accumulators complete
+                __syncwarp();
             }
         }
     } else if (lane == 0) {
@@ -656,10 +671,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
             mbar_arrive(smem_u32(&sh->tmem_empty[buf]));
         }
     } else if (warp == kWideEpiWarps) {
-        // ===================================================== UMMA issuer
-        if (lane == 0) {
+        // ===================================================== UMMA issuer (whole warp in the loop, one lane issues)
+        {
             int it = 0;
             uint32_t kcount = 0;
+            const uint32_t tbase = __shfl_sync(kFull, tmem_base, 0);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t par = (it >> 1) & 1;
@@ -669,7 +685,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
                 mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);
                 tc_fence_after();
                 for (int h = 0; h < g.H; ++h) {
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * accw + h * g.BN);
+                    const uint32_t tmem_d = tbase + (uint32_t)(buf * accw + h * g.BN);
                     for (int kb = 0; kb < nkb; ++kb, ++kcount) {
                         const int s = kcount % g.stages;
                         const uint32_t sp = (kcount / g.stages) & 1;
@@ -679,19 +695,23 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_kernel(const __grid_cons
                         const uint32_t a_lo = a_hi + BM * 128;
                         const uint32_t b_hi = a_hi + kABytes;
                         const uint32_t b_lo = b_hi + g.BN * 128;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint32_t ko = k * 32;
-                            const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
-                            const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
-                            umma_bf16(tmem_d, dah, dbh, idesc, (kb | k) != 0);
-                            umma_bf16(tmem_d, dah, dbl, idesc, 1);
-                            umma_bf16(tmem_d, dal, dbh, idesc, 1);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint32_t ko = k * 32;
+                                const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                                const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                                umma_bf16(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                                umma_bf16(tmem_d, dah, dbl, idesc, 1);
+                                umma_bf16(tmem_d, dal, dbh, idesc, 1);
+                            }
+                            umma_commit(smem_u32(&sh->empty[s]));
                         }
-                        umma_commit(smem_u32(&sh->empty[s]));
+                        __syncwarp();
                     }
                 }
-                umma_commit(smem_u32(&sh->tmem_full[buf]));
+                if (elect_one()) umma_commit(smem_u32(&sh->tmem_full[buf]));
+                __syncwarp();
             }
         }
     } else if (lane == 0) {
@@ -796,18 +816,19 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_pair_kernel(const __grid
             if (lane == 0) mbar_arrive_cluster(buf ? empty_leader1 : empty_leader0);
         }
     } else if (warp == kWideEpiWarps) {
-        // ===================================================== UMMA issuer (leader, one thread)
-        if (leader && lane == 0) {
+        // ===================================================== UMMA issuer (leader; whole warp in the loop, one lane issues)
+        if (leader) {
             int it = 0;
             uint32_t kcount = 0;
             const uint32_t idesc = make_idesc_pair(g.BN);
+            const uint32_t tbase = __shfl_sync(kFull, tmem_base, 0);
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
                 const int buf = it & 1;
                 const uint32_t par = (it >> 1) & 1;
                 mbar_wait(smem_u32(&sh->tmem_empty[buf]), par ^ 1);
                 tc_fence_after();
                 for (int h = 0; h < g.H; ++h) {
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * accw + h * g.BN);
+                    const uint32_t tmem_d = tbase + (uint32_t)(buf * accw + h * g.BN);
                     for (int kb = 0; kb < nkb; ++kb, ++kcount) {
                         const int s = kcount % g.stages;
                         const uint32_t sp = (kcount / g.stages) & 1;
@@ -817,19 +838,23 @@ __global__ void __launch_bounds__(kWideThreads, 1) wide_pair_kernel(const __grid
                         const uint32_t a_lo = a_hi + BM * 128;
                         const uint32_t b_hi = a_hi + kABytes;
                         const uint32_t b_lo = b_hi + half * 128;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint32_t ko = k * 32;
-                            const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
-                            const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
-                            umma_bf16_pair(tmem_d, dah, dbh, idesc, (kb | k) != 0);
-                            umma_bf16_pair(tmem_d, dah, dbl, idesc, 1);
-                            umma_bf16_pair(tmem_d, dal, dbh, idesc, 1);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint32_t ko = k * 32;
+                                const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                                const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                                umma_bf16_pair(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+                                umma_bf16_pair(tmem_d, dah, dbl, idesc, 1);
+                                umma_bf16_pair(tmem_d, dal, dbh, idesc, 1);
+                            }
+                            umma_commit_pair(smem_u32(&sh->empty[s]), 3);
                         }
-                        umma_commit_pair(smem_u32(&sh->empty[s]), 3);
+                        __syncwarp();
                     }
                 }
-                umma_commit_pair(smem_u32(&sh->tmem_full[buf]), 3);
+                if (elect_one()) umma_commit_pair(smem_u32(&sh->tmem_full[buf]), 3);
+                __syncwarp();
             }
         }
     } else if (lane == 0) {
@@ -1015,14 +1040,17 @@ __global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_con
         }
       }
     } else if (warp == kEpiWarps) {
-        if (lane == 0) {
+        // UMMA issuer: the whole warp walks the loop, one elected lane issues (see nt_pair_kernel)
+        {
             const uint32_t idesc = make_idesc(n_mma, true);
+            const uint32_t tbase = __shfl_sync(kFull, tmem_base, 0);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T_STAGES;
                 const uint32_t sp = (kb / T_STAGES) & 1;
                 const int kin = kb % g.flush_kb;            // position inside the accumulation chunk
                 if (kb > 0 && kin == 0) {
-                    umma_commit(smem_u32(&sh->tmem_full));
+                    if (elect_one()) umma_commit(smem_u32(&sh->tmem_full));
+                    __syncwarp();
                     mbar_wait(smem_u32(&sh->tmem_empty), ((kb / g.flush_kb) - 1) & 1);
                     tc_fence_after();
                 }
@@ -1030,24 +1058,28 @@ __global__ void __launch_bounds__(kThreads, 1) tn_planes_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t p_base = smem_base + s * T_STAGE;
                 const uint32_t q_base = p_base + 4 * T_BLK;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < T_BK / 16; ++k) {
-                    const uint32_t ko = k * 16 * 128;            // 16 node rows of 128 B
-                    // MN-major SW128: 64-column blocks T_BLK apart (LBO), 8-row groups 1 KB apart (SBO)
-                    const uint64_t dbh = make_desc(q_base + ko, T_BLK, 1024);
-                    const uint64_t dbl = make_desc(q_base + T_BLK / 2 + ko, T_BLK, 1024);
-                    for (int acc = 0; acc < nacc; ++acc) {
-                        const uint32_t ao = p_base + acc * 2 * T_BLK + ko;
-                        const uint64_t dah = make_desc(ao, T_BLK, 1024), dal = make_desc(ao + T_BLK / 2, T_BLK, 1024);
-                        const uint32_t td = tmem_base + (uint32_t)(acc * 256);
-                        umma_bf16(td, dah, dbh, idesc, (kin | k) != 0);
-                        umma_bf16(td, dah, dbl, idesc, 1);
-                        umma_bf16(td, dal, dbh, idesc, 1);
+                    for (int k = 0; k < T_BK / 16; ++k) {
+                        const uint32_t ko = k * 16 * 128;            // 16 node rows of 128 B
+                        // MN-major SW128: 64-column blocks T_BLK apart (LBO), 8-row groups 1 KB apart (SBO)
+                        const uint64_t dbh = make_desc(q_base + ko, T_BLK, 1024);
+                        const uint64_t dbl = make_desc(q_base + T_BLK / 2 + ko, T_BLK, 1024);
+                        for (int acc = 0; acc < nacc; ++acc) {
+                            const uint32_t ao = p_base + acc * 2 * T_BLK + ko;
+                            const uint64_t dah = make_desc(ao, T_BLK, 1024), dal = make_desc(ao + T_BLK / 2, T_BLK, 1024);
+                            const uint32_t td = tbase + (uint32_t)(acc * 256);
+                            umma_bf16(td, dah, dbh, idesc, (kin | k) != 0);
+                            umma_bf16(td, dah, dbl, idesc, 1);
+                            umma_bf16(td, dal, dbh, idesc, 1);
+                        }
                     }
+                    umma_commit(smem_u32(&sh->empty[s]));
                 }
-                umma_commit(smem_u32(&sh->empty[s]));
+                __syncwarp();
             }
-            if (nkb > 0) umma_commit(smem_u32(&sh->tmem_full));
+            if (nkb > 0 && elect_one()) umma_commit(smem_u32(&sh->tmem_full));
+            __syncwarp();
         }
     } else if (lane == 0) {
         const uint32_t tx = (uint32_t)(npb + nqb) * T_BLK;

@@ -68,6 +68,17 @@ __device__ __forceinline__ void cluster_sync_all() {          // every thread of
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// one lane of a converged warp (the same lane every time): the issuing thread of the single-thread tcgen05 / TMA paths
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
