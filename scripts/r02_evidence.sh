@@ -10,7 +10,7 @@ timeout 900 python bench.py --steps 10 --warmup 3 > ${P}_bench.json 2>> ${P}_ben
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file ${P}_launches.csv \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-small --stream-steps 0 > ${P}_b_ncu.log 2>&1
 python scripts/launch_summary.py ${P}_launches.csv > ${P}_launches_summary.txt 2>&1; head -14 ${P}_launches_summary.txt
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'nt_planes_kernel|tn_planes_kernel|wide_kernel|gat_tree_fwd_kernel|gat_tree_bwd_kernel|aggx_|split_planes_kernel|reduce_splits' \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'nt_planes_kernel|nt_pair_kernel|tn_planes_kernel|wide_kernel|gat_tree_fwd_kernel|gat_tree_bwd_kernel|aggx_|split_planes_kernel|reduce_splits' \
   --launch-skip 95 --launch-count 60 -o /tmp/full_step -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-small --stream-steps 0 > ${P}_b_full.log 2>&1
 ls -la /tmp/full_step.ncu-rep
 python scripts/ncu_traffic.py /tmp/full_step.ncu-rep ${P}_ncu_traffic.json 4096 > ${P}_ncu_table.txt 2>&1; cat ${P}_ncu_table.txt
