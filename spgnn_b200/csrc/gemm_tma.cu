@@ -1225,6 +1225,31 @@ static unsigned split_grid(int64_t total) {
     return (unsigned)(want < cap ? want : cap);
 }
 
+// Co-resident 2-CTA clusters of a pair kernel on the CURRENT device (0: cluster launches unavailable / disabled).  Cached
+// per device ordinal: the dynamic-shared-memory opt-in and the occupancy are per-device properties.
+template <typename Kernel>
+static int pair_clusters_of(Kernel kernel, int threads, const char* env, bool default_on, int* cache /* [64], -1 */) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    if (cache[dev] >= 0) return cache[dev];
+    int n = 0;
+    const char* e = getenv(env);
+    const bool on = e ? atoi(e) != 0 : default_on;
+    if (on && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) == cudaSuccess) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = kSmemLimit; cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) n = 0;
+    }
+    (void)cudaGetLastError();
+    cache[dev] = n;
+    return n;
+}
+struct PairCache { int v[64]; PairCache() { for (int& x : v) x = -1; } };
+
 // C = [A1|A2] * Bplanes^T with Bplanes [N, ldb] already split (hi at Bhi, lo at Bhi + N*ldb)
 static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t K1, const __nv_bfloat16* A2,
                      int64_t lda2, int64_t ps2, int64_t K2, const __nv_bfloat16* Bhi, int64_t ldb, const float* bias,
@@ -1255,23 +1280,8 @@ static int launch_nt(const __nv_bfloat16* A1, int64_t lda1, int64_t ps1, int64_t
     NtArgs a{};
     pick_bn((int)N, &a.BN, &a.nt_n);
     // CTA pairs (cta_group::2) unless SPGNN_NT_PAIR=0
-    static int pair_clusters = -1;
-    if (pair_clusters < 0) {
-        pair_clusters = 0;
-        const char* e = getenv("SPGNN_NT_PAIR");
-        if (!e || atoi(e) != 0) {
-            SPGNN_CUDA_OK(cudaFuncSetAttribute(nt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-            cudaLaunchConfig_t cfg{};
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(kThreads);
-            cfg.dynamicSmemBytes = kSmemLimit; cfg.attrs = at; cfg.numAttrs = 1;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, nt_pair_kernel, &cfg) == cudaSuccess) pair_clusters = n;
-            else (void)cudaGetLastError();
-        }
-    }
+    static PairCache pair_cache;
+    const int pair_clusters = pair_clusters_of(nt_pair_kernel, kThreads, "SPGNN_NT_PAIR", true, pair_cache.v);
     // Measured on 1.23 M rows (profiles/r02_nt_pair_vs_single.txt): gat0 / gat1 forward -6..-12 % / -19..-25 %, dX of
     // gat1 / the output layer (K = 4100 -> 192 columns) -17..-21 % / -28 %; output-bound shapes (small K: pgnn0-2,
     // K = 192 -> 4100 columns) lose 10 - 30 % to the coupling of the two epilogues and stay on the single-CTA kernel
@@ -1477,23 +1487,8 @@ extern "C" int spgnn_wide_linear(const uint16_t* XA, int64_t ldxa, int64_t psxa,
     // the bench size -- forward 5.71 -> 6.05 ms, backward 6.52 -> 7.54 ms (profiles/r02_wide_pair_probe.txt): with
     // BN = 128 and a 16-warp epilogue per CTA the leader's wait for BOTH epilogues costs more than the halved weight
     // traffic saves.  Needs F % BN == 0 (every CTA loads exactly half a weight tile) and enough m-tiles for every pair
-    static int pair_clusters = -1;
-    if (pair_clusters < 0) {
-        pair_clusters = 0;
-        const char* e = getenv("SPGNN_WIDE_PAIR");
-        if (e && atoi(e) == 1) {
-            SPGNN_CUDA_OK(cudaFuncSetAttribute(wide_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-            cudaLaunchConfig_t cfg{};
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(kWideThreads);
-            cfg.dynamicSmemBytes = kSmemLimit; cfg.attrs = at; cfg.numAttrs = 1;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, wide_pair_kernel, &cfg) == cudaSuccess) pair_clusters = n;
-            else (void)cudaGetLastError();
-        }
-    }
+    static PairCache pair_cache;
+    const int pair_clusters = pair_clusters_of(wide_pair_kernel, kWideThreads, "SPGNN_WIDE_PAIR", false, pair_cache.v);
     const bool pair = pair_clusters > 0 && F % a.BN == 0 && a.BN % 32 == 0 && a.nt_m >= 4 * (int64_t)pair_clusters;
     if (pair) {
         rc = make_planes_map(&maps.b, hi, HF, ldb, ldb, HF * ldb, BK, a.BN / 2);
