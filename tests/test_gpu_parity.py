@@ -831,3 +831,38 @@ def test_dx_gemm_with_the_consumer_dropout_mask_in_its_epilogue(mods, M, N, K, k
     assert torch.equal(masked[:, :K], torch.where(keep != 0, plain[:, :K] * scale, torch.zeros_like(plain[:, :K])))
     again = stack.planes_linear_bwd_input(dC, W, K, k_off=k_off, drop_p=p, seed=seed + 1, concat_chunks=cc)
     assert not torch.equal(again[:, :K], masked[:, :K])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,K1,K2,N", [(38017, 512, 256, 516), (40100, 1024, 39, 1028), (37889 + 128, 256, 0, 384)])
+def test_cta_pair_projection_gemm_against_fp64_and_the_single_cta_kernel(mods, M, K1, K2, N):
+    """nt_pair_kernel (tcgen05 cta_group::2; taken for K >= 256 and N >= 320 once there are >= 4 m-tiles per pair) on
+    shapes with an odd number of m-tiles, a ragged last tile and concatenated sources: forward (with bias + ELU in the
+    epilogue) and dX against fp64, and bit-for-bit against the same rows pushed through the single-CTA kernel in
+    batches too small for the pair path (the projections of GATConv, models.py:301-314 through DGL's fc / res_fc)."""
+    from spgnn_b200 import stack
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator().manual_seed(M)
+    x1 = torch.randn(M, K1, generator=gen).to(dev)
+    x2 = torch.randn(M, (K2 + 3) // 4 * 4, generator=gen)[:, :K2].to(dev) if K2 else None
+    W = (torch.randn(N, K1 + K2, generator=gen) / (K1 + K2) ** 0.5).to(dev)
+    b = torch.randn(N, generator=gen).to(dev)
+    P1, P2 = stack.split_planes(x1), (stack.split_planes(x2) if K2 else None)
+    y = stack.planes_linear(P1, W, bias=b, act=1, A2=P2)
+    xd = torch.cat([x1, x2], 1).double() if K2 else x1.double()
+    ref = torch.nn.functional.elu(xd @ W.double().t() + b.double())
+    assert rel_err(y[:, :N].cpu(), ref.cpu()) < 4e-5
+    go = stack.split_planes(torch.randn(M, N, generator=gen).to(dev))
+    dx = stack.planes_linear_bwd_input(go, W, K1 + K2)
+    assert rel_err(dx[:, :K1 + K2].cpu(), (go.float().double() @ W.double()).cpu()) < 4e-5
+    # the same rows through the single-CTA kernel (small batches never take the pair path): identical bits
+    rows = slice(M - 3000, M)
+    Ps = stack.split_planes(x1[rows].contiguous())
+    P2s = stack.split_planes(x2[rows].contiguous()) if K2 else None
+    ys = stack.planes_linear(Ps, W, bias=b, act=1, A2=P2s)
+    assert torch.equal(ys[:, :N], y[rows, :N])
+    # masked epilogue on the pair path == mask applied afterwards
+    dxm = stack.planes_linear_bwd_input(go, W, K1 + K2, drop_p=0.1, seed=99)
+    keep = stack.split_planes(torch.ones(M, K1 + K2, device=dev), p=0.1, seed=99).float()
+    scale = torch.tensor(1.0, device=dev) / (torch.tensor(1.0, device=dev) - torch.tensor(0.1, device=dev))
+    assert torch.equal(dxm[:, :K1 + K2], torch.where(keep != 0, dx[:, :K1 + K2] * scale, torch.zeros_like(dx[:, :K1 + K2])))
