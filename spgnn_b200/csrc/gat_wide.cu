@@ -13,6 +13,7 @@
 // and stages neighbour ids and weights of the <= 4 edges in shared memory; phase B is warp-per-node over 128-bit
 // column chunks.  HBM roofline: rows are k_in (192) wide, so all three kernels together move ~6 KB per node —
 // 5 % of what the projection-first layer kernels moved for the same layer.
+#include <stdlib.h>
 #include "layer_util.cuh"
 
 namespace spgnn {
@@ -85,8 +86,23 @@ static size_t stage_bytes(int H, int k4) {
 // the forward only stages deg | beg | nb | w (at / lk / dd / we belong to the backward): independent of k_in
 static size_t stage_bytes_fwd(int H) { return (size_t)kNPC * 6 * 4 + (size_t)kNPC * H * 4 * 4 + 16; }
 
+
+// Phase B of the three kernels runs LPN lanes per node (32: one warp per node; 16: two nodes per warp).  The output
+// layer's input is 192 columns = 48 four-column chunks: with 32 lanes the second pass of the chunk loop leaves half the
+// warp idle, with 16 lanes every pass is full.
+template <int LPN>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+    for (int o = LPN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <int LPN>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    return LPN == 32 ? 0xFFFFFFFFu : (0xFFFFu << (lane & 16));
+}
+
 // ------------------------------------------------------------------------------------------------ forward
-template <int H>
+template <int H, int LPN>
 __global__ void __launch_bounds__(kThreads) aggx_fwd_kernel(const WArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const Stage st = carve(smem, H);
@@ -138,9 +154,10 @@ __global__ void __launch_bounds__(kThreads) aggx_fwd_kernel(const WArgs a) {
         }
         __syncthreads();
         // ---------------- phase B: Ax_h for every head + the copy of x, one warp per node
-        for (int n = warp; n < kNPC; n += kThreads / 32) {
+        for (int n = warp * (32 / LPN) + lane / LPN; n < kNPC; n += kThreads / LPN) {
             const int64_t v = base + n;
-            if (v >= a.N) break;
+            if (v >= a.N) continue;
+            const int gl = lane & (LPN - 1);
             const int deg = st.deg[n];
             __nv_bfloat16* orow = a.XA + v * a.ldxa;
             if (deg <= 4) {
@@ -148,7 +165,7 @@ __global__ void __launch_bounds__(kThreads) aggx_fwd_kernel(const WArgs a) {
                 float4 w[H];
 #pragma unroll
                 for (int h = 0; h < H; ++h) w[h] = *reinterpret_cast<const float4*>(st.w + (n * H + h) * 4);
-                for (int ch = lane; ch < nch; ch += 32) {
+                for (int ch = gl; ch < nch; ch += LPN) {
                     const int c = ch * 4;
                     const float4 x0 = load_x(a, nb.x, c), x1 = load_x(a, nb.y, c), x2 = load_x(a, nb.z, c),
                                  x3 = load_x(a, nb.w, c);
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) aggx_fwd_kernel(const WArgs a) {
                 }
             } else {
                 const int beg = st.beg[n];
-                for (int ch = lane; ch < nch; ch += 32) {
+                for (int ch = gl; ch < nch; ch += LPN) {
                     const int c = ch * 4;
 #pragma unroll
                     for (int h = 0; h < H; ++h) {
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) aggx_fwd_kernel(const WArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward, dst side
-template <int H>
+template <int H, int LPN>
 __global__ void __launch_bounds__(kThreads) aggx_bwd_dst_kernel(const WArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const Stage st = carve(smem, H);
@@ -213,16 +230,18 @@ __global__ void __launch_bounds__(kThreads) aggx_bwd_dst_kernel(const WArgs a) {
         }
         __syncthreads();
         // ---------------- phase B: <d(Ax_h)[v], x[u_j]> for the (<= 4) in-edges of v
-        for (int n = warp; n < kNPC; n += kThreads / 32) {
+        for (int n = warp * (32 / LPN) + lane / LPN; n < kNPC; n += kThreads / LPN) {
             const int64_t v = base + n;
-            if (v >= a.N) break;
+            if (v >= a.N) continue;
+            const int gl = lane & (LPN - 1);
+            const unsigned gm = group_mask<LPN>(lane);
             const int deg = st.deg[n];
             if (deg <= 4) {
                 const int4 nb = *reinterpret_cast<const int4*>(st.nb + n * 4);
                 float d[H][4];
 #pragma unroll
                 for (int h = 0; h < H; ++h) d[h][0] = d[h][1] = d[h][2] = d[h][3] = 0.f;
-                for (int ch = lane; ch < nch; ch += 32) {
+                for (int ch = gl; ch < nch; ch += LPN) {
                     const int c = ch * 4;
                     const float4 x0 = load_xa(a, nb.x, c), x1 = load_xa(a, nb.y, c), x2 = load_xa(a, nb.z, c),
                                  x3 = load_xa(a, nb.w, c);
@@ -234,8 +253,9 @@ __global__ void __launch_bounds__(kThreads) aggx_bwd_dst_kernel(const WArgs a) {
                 }
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
-                    const float d0 = warp_sum(d[h][0]), d1 = warp_sum(d[h][1]), d2 = warp_sum(d[h][2]), d3 = warp_sum(d[h][3]);
-                    if (lane == 0) *reinterpret_cast<float4*>(st.dd + (n * H + h) * 4) = make_float4(d0, d1, d2, d3);
+                    const float d0 = group_sum<LPN>(d[h][0], gm), d1 = group_sum<LPN>(d[h][1], gm),
+                                d2 = group_sum<LPN>(d[h][2], gm), d3 = group_sum<LPN>(d[h][3], gm);
+                    if (gl == 0) *reinterpret_cast<float4*>(st.dd + (n * H + h) * 4) = make_float4(d0, d1, d2, d3);
                 }
             } else {
                 const int beg = st.beg[n];
@@ -243,10 +263,10 @@ __global__ void __launch_bounds__(kThreads) aggx_bwd_dst_kernel(const WArgs a) {
                     for (int s = beg; s < beg + deg; ++s) {
                         const int u = __ldg(a.in_src + s);
                         float dsum = 0.f;
-                        for (int ch = lane; ch < nch; ch += 32)
+                        for (int ch = gl; ch < nch; ch += LPN)
                             dsum += dot4(ldg4(a.dXA + h * a.head_stride + v * a.ld_dxa + ch * 4), load_xa(a, u, ch * 4));
-                        dsum = warp_sum(dsum);
-                        if (lane == 0) a.ds[(int64_t)s * H + h] = dsum * keep_scale(a, s, h);
+                        dsum = group_sum<LPN>(dsum, gm);
+                        if (gl == 0) a.ds[(int64_t)s * H + h] = dsum * keep_scale(a, s, h);
                     }
             }
         }
@@ -294,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) aggx_bwd_dst_kernel(const WArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward, src side
-template <int H>
+template <int H, int LPN>
 __global__ void __launch_bounds__(kThreads) aggx_bwd_src_kernel(const WArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const Stage st = carve(smem, H);
@@ -337,9 +357,10 @@ __global__ void __launch_bounds__(kThreads) aggx_bwd_src_kernel(const WArgs a) {
             store_planes1(a.dep + u * a.ld_dep + H + h, a.ps_dep, der);
         }
         __syncthreads();
-        for (int n = warp; n < kNPC; n += kThreads / 32) {
+        for (int n = warp * (32 / LPN) + lane / LPN; n < kNPC; n += kThreads / LPN) {
             const int64_t u = base + n;
-            if (u >= a.N) break;
+            if (u >= a.N) continue;
+            const int gl = lane & (LPN - 1);
             const int deg = st.deg[n];
             float del[H], der[H];
 #pragma unroll
@@ -350,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) aggx_bwd_src_kernel(const WArgs a) {
                 float4 w[H];
 #pragma unroll
                 for (int h = 0; h < H; ++h) w[h] = *reinterpret_cast<const float4*>(st.w + (n * H + h) * 4);
-                for (int ch = lane; ch < nch; ch += 32) {
+                for (int ch = gl; ch < nch; ch += LPN) {
                     const int c = ch * 4;
                     float4 acc = zero4();
 #pragma unroll
@@ -368,7 +389,7 @@ __global__ void __launch_bounds__(kThreads) aggx_bwd_src_kernel(const WArgs a) {
                 }
             } else {
                 const int beg = st.beg[n];
-                for (int ch = lane; ch < nch; ch += 32) {
+                for (int ch = gl; ch < nch; ch += LPN) {
                     const int c = ch * 4;
                     float4 acc = zero4();
 #pragma unroll
@@ -445,13 +466,29 @@ using namespace spgnn::wide;
 
 extern "C" int64_t spgnn_gat_wide_sizeof(void) { return (int64_t)sizeof(spgnn_gat_wide); }
 
-#define WIDE_DISPATCH(KERNEL, ...)                                          \
+// NCH = four-column chunks per row: 16 lanes per node when that fills every pass of the chunk loop and 32 would not
+#define WIDE_DISPATCH_H(KERNEL, HH, NCH, ...)                                                   \
+    do {                                                                                        \
+        if ((NCH) % 32 != 0 && (NCH) % 16 == 0 && wide_lanes_per_node() != 32)                  \
+            KERNEL<HH, 16><<<grid, kThreads, smem, st>>>(__VA_ARGS__);                          \
+        else KERNEL<HH, 32><<<grid, kThreads, smem, st>>>(__VA_ARGS__);                         \
+    } while (0)
+#define WIDE_DISPATCH(KERNEL, NCH, ...)                                     \
     do {                                                                    \
-        if (a.H == 1) KERNEL<1><<<grid, kThreads, smem, st>>>(__VA_ARGS__); \
-        else if (a.H == 2) KERNEL<2><<<grid, kThreads, smem, st>>>(__VA_ARGS__); \
-        else KERNEL<4><<<grid, kThreads, smem, st>>>(__VA_ARGS__);          \
+        if (a.H == 1) WIDE_DISPATCH_H(KERNEL, 1, NCH, __VA_ARGS__);         \
+        else if (a.H == 2) WIDE_DISPATCH_H(KERNEL, 2, NCH, __VA_ARGS__);    \
+        else WIDE_DISPATCH_H(KERNEL, 4, NCH, __VA_ARGS__);                  \
         SPGNN_LAUNCH_OK();                                                  \
     } while (0)
+// SPGNN_AGGX_LANES=32 forces one warp per node (A/B runs)
+static int wide_lanes_per_node() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SPGNN_AGGX_LANES");
+        v = (e && atoi(e) == 32) ? 32 : 16;
+    }
+    return v;
+}
 
 extern "C" int spgnn_gat_aggx_fwd(const spgnn_gat_wide* L, void* stream) {
     WArgs a{};
@@ -460,7 +497,7 @@ extern "C" int spgnn_gat_aggx_fwd(const spgnn_gat_wide* L, void* stream) {
     cudaStream_t st = as_stream(stream);
     const unsigned grid = wide_grid(a.N);
     const size_t smem = stage_bytes_fwd(a.H);
-    WIDE_DISPATCH(aggx_fwd_kernel, a);
+    WIDE_DISPATCH(aggx_fwd_kernel, a.kp >> 2, a);
     return SPGNN_OK;
 }
 
@@ -472,8 +509,8 @@ extern "C" int spgnn_gat_aggx_bwd(const spgnn_gat_wide* L, void* stream) {
     const unsigned grid = wide_grid(a.N);
     const size_t smem = stage_bytes(a.H, a.k4);
     SPGNN_REQUIRE(smem <= 48 * 1024, "gat_aggx_bwd: k_in too large for the logit-weight stage (%zu bytes)", smem);
-    WIDE_DISPATCH(aggx_bwd_dst_kernel, a);
-    WIDE_DISPATCH(aggx_bwd_src_kernel, a);
+    WIDE_DISPATCH(aggx_bwd_dst_kernel, a.k4 >> 2, a);
+    WIDE_DISPATCH(aggx_bwd_src_kernel, a.k4 >> 2, a);
     return SPGNN_OK;
 }
 
