@@ -177,7 +177,9 @@ int spgnn_act_bwd_planes(const float* g, int64_t ldg, const float* y, int64_t ld
                          int64_t M, int64_t N, float* colsum_out, void* ws, void* stream);
 /* The launch plan planes_linear_bwd_weight would use (host only, no device work; for tests and profiling):
  * out[0..7] = {swap (1: the gradient dC is the M-side operand), np_tiles, nq_tiles, row splits, CTAs, rows per
- * split, 64-column blocks on the M side, on the N side}.  Returns the number of ints written (8). */
+ * split, 64-column blocks on the M side, on the N side} and, when cap >= 9, out[8] = 1 if the two sources X1 / X2 get
+ * one launch each (their blocks tile badly together; out[0..7] then describe the first launch, X1 alone).  Returns the
+ * number of ints written (8 or 9). */
 int64_t spgnn_planes_linear_bwd_weight_plan(int64_t M, int64_t N, int64_t K1, int64_t K2, int32_t* out, int64_t cap);
 
 /* out[n] = sum_m X[m, n]  (bias gradients).  ws: spgnn_colsum_ws(N) bytes. */

@@ -1566,6 +1566,7 @@ struct TnPlan {
     bool swap;                 // false: P = X (k), Q = dC (n) -> out[q][p];  true: P = dC, Q = X -> out[p][q]
     int npb, nqb, np_tiles, nq_tiles;
     int64_t splits, rows;
+    double cost;               // modelled cycles of the launch (tile cost x stages per row range); < 0: not modelled
 };
 // 64-column blocks of up to two concatenated sources, with the valid columns of each block
 int blocks_of(int64_t c0, int64_t c1, int* valid) {
@@ -1628,7 +1629,7 @@ TnPlan tn_plan(int64_t M, int64_t N, int64_t K1, int64_t K2) {
         if (best_t < 0.0 || t < 0.97 * best_t) {          // P = X unless the flip is clearly better
             best_t = t;
             best.swap = sw != 0; best.npb = npb; best.nqb = nqb; best.np_tiles = npt; best.nq_tiles = nqt;
-            best.splits = splits; best.rows = rows;
+            best.splits = splits; best.rows = rows; best.cost = t;
         }
     }
     if (best_t >= 0.0) return best;
@@ -1640,7 +1641,24 @@ TnPlan tn_plan(int64_t M, int64_t N, int64_t K1, int64_t K2) {
     t.nq_tiles = (int)ceil_div(t.nqb, 4);
     t.rows = ceil_div(M, T_BK) * T_BK;
     t.splits = 1;
+    t.cost = -1.0;
     return t;
+}
+// Two concatenated sources whose block counts do not tile well TOGETHER are better served by two launches: gat0's
+// X = [fvs 1024 | pos_enc 39] is 16 + 1 blocks, and 17 x 17 blocks make 25 tiles x 5 row ranges = 125 of 148 SMs with a
+// half-empty accumulator on every 3-block tile, while 16 x 17 blocks make 20 tiles x 7 row ranges = 140 SMs of full
+// tiles (model: 6.5 -> 4.6 + 0.7 ms).  Taken when the model rates the pair of launches at least 8 % cheaper.
+bool tn_split_sources(int64_t M, int64_t N, int64_t K1, int64_t K2) {
+    if (K2 <= 0) return false;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("SPGNN_TN_SPLIT_SOURCES");
+        enabled = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (!enabled) return false;
+    const TnPlan both = tn_plan(M, N, K1, K2), a = tn_plan(M, N, K1, 0), b = tn_plan(M, N, K2, 0);
+    if (both.cost < 0.0 || a.cost < 0.0 || b.cost < 0.0) return false;
+    return a.cost + b.cost < 0.92 * both.cost;
 }
 }  // namespace
 
@@ -1661,24 +1679,37 @@ static int64_t tn_chunks_per_split(const TnPlan& t) {
     return c < 1 ? 1 : c;
 }
 
-extern "C" int64_t spgnn_planes_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K1, int64_t K2) {
+static int64_t tn_ws_one(int64_t M, int64_t N, int64_t K1, int64_t K2) {
     const TnPlan t = tn_plan(M, N, K1, K2);
     return t.splits * tn_chunks_per_split(t) * N * (K1 + K2) * (int64_t)sizeof(float) + 256;
+}
+extern "C" int64_t spgnn_planes_linear_bwd_weight_ws(int64_t M, int64_t N, int64_t K1, int64_t K2) {
+    if (tn_split_sources(M, N, K1, K2)) {
+        const int64_t a = tn_ws_one(M, N, K1, 0), b = tn_ws_one(M, N, K2, 0);
+        return a > b ? a : b;
+    }
+    return tn_ws_one(M, N, K1, K2);
 }
 
 extern "C" int64_t spgnn_planes_linear_bwd_weight_plan(int64_t M, int64_t N, int64_t K1, int64_t K2, int32_t* out,
                                                        int64_t cap) {
     if (!out || cap < 8 || M <= 0 || N <= 0 || K1 <= 0 || K2 < 0) return 0;
-    const TnPlan t = tn_plan(M, N, K1, K2);
+    const bool split = tn_split_sources(M, N, K1, K2);      // then: the plan of the FIRST launch (X1 alone)
+    const TnPlan t = tn_plan(M, N, K1, split ? 0 : K2);
+    if (cap >= 9) out[8] = split ? 1 : 0;
     const int tiles = t.np_tiles * t.nq_tiles;
     const int64_t work = (int64_t)tiles * t.splits;
     const int32_t head[8] = {t.swap, t.np_tiles, t.nq_tiles, (int32_t)t.splits, (int32_t)work, (int32_t)t.rows, t.npb, t.nqb};
     int64_t n = 0;
     for (; n < 8 && n < cap; ++n) out[n] = head[n];
-    return n;
+    return cap >= 9 ? 9 : n;
 }
 
 // dW[N, K1+K2] (lddw) = dC[M, N]^T * [X1 | X2][M, K1+K2], every operand in planes form
+static int tn_launch(const uint16_t* dC, int64_t lddc, int64_t psc, const uint16_t* X1, int64_t ldx1, int64_t psx1,
+                     int64_t K1, const uint16_t* X2, int64_t ldx2, int64_t psx2, int64_t K2, float* dW, int64_t lddw,
+                     int64_t M, int64_t N, void* ws, void* stream);
+
 extern "C" int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, int64_t psc, const uint16_t* X1,
                                               int64_t ldx1, int64_t psx1, int64_t K1, const uint16_t* X2, int64_t ldx2,
                                               int64_t psx2, int64_t K2, float* dW, int64_t lddw, int64_t M, int64_t N,
@@ -1688,6 +1719,17 @@ extern "C" int spgnn_planes_linear_bwd_weight(const uint16_t* dC, int64_t lddc, 
     SPGNN_REQUIRE(lddw >= K1 + K2, "planes_linear_bwd_weight: leading dimension too small");
     SPGNN_REQUIRE(ws_bytes >= spgnn_planes_linear_bwd_weight_ws(M, N, K1, K2), "planes_linear_bwd_weight: workspace too small");
     SPGNN_REQUIRE(M < (1ll << 31), "planes_linear_bwd_weight: too many rows");
+    if (tn_split_sources(M, N, K1, K2)) {        // one launch per source (stream-ordered, the workspace is reused)
+        int rc = tn_launch(dC, lddc, psc, X1, ldx1, psx1, K1, nullptr, 0, 0, 0, dW, lddw, M, N, ws, stream);
+        if (rc) return rc;
+        return tn_launch(dC, lddc, psc, X2, ldx2, psx2, K2, nullptr, 0, 0, 0, dW + K1, lddw, M, N, ws, stream);
+    }
+    return tn_launch(dC, lddc, psc, X1, ldx1, psx1, K1, X2, ldx2, psx2, K2, dW, lddw, M, N, ws, stream);
+}
+
+static int tn_launch(const uint16_t* dC, int64_t lddc, int64_t psc, const uint16_t* X1, int64_t ldx1, int64_t psx1,
+                     int64_t K1, const uint16_t* X2, int64_t ldx2, int64_t psx2, int64_t K2, float* dW, int64_t lddw,
+                     int64_t M, int64_t N, void* ws, void* stream) {
     static DeviceOnce attr;
     if (attr.pending()) {
         SPGNN_CUDA_OK(cudaFuncSetAttribute(tn_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));

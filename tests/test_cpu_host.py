@@ -130,19 +130,24 @@ def test_weight_gradient_launch_plan_is_sane():
     shapes = {"gat0": (1028, 1024, 39), "gat1": (516, 512, 256), "gat2": (260, 256, 128), "pgnn0": (514, 39, 0),
               "pgnn1": (258, 256, 0), "pgnn2": (130, 128, 0), "head": (22, 1024, 0), "gat_out_head": (1024, 192, 192)}
     plans = {}
+    split_sources = {}
     for name, (N, K1, K2) in shapes.items():
-        out = (ctypes.c_int32 * 8)()
-        assert L.planes_linear_bwd_weight_plan(M, N, K1, K2, out, 8) == 8
-        swap, npt, nqt, splits, ctas, rows, npb, nqb = list(out)
-        plans[name] = swap
+        out = (ctypes.c_int32 * 9)()
+        assert L.planes_linear_bwd_weight_plan(M, N, K1, K2, out, 9) == 9
+        swap, npt, nqt, splits, ctas, rows, npb, nqb, split = list(out)
+        plans[name], split_sources[name] = swap, split
         assert 1 <= ctas <= 148 and ctas == npt * nqt * splits
         assert rows % 32 == 0 and rows * splits >= M > rows * (splits - 1)
         assert npt == -(-npb // 4) and nqt == -(-nqb // 4)
-        xb = -(-K1 // 64) + (-(-K2 // 64) if K2 else 0)
+        # split == 1: one launch per source, the plan is the first one's (X1 alone)
+        xb = -(-K1 // 64) + (-(-K2 // 64) if K2 and not split else 0)
         yb = -(-N // 64)
         assert (npb, nqb) == ((yb, xb) if swap else (xb, yb))
     # X = [Ax_h | x] is 3 + 3 blocks: on the M side it fills 1.5 accumulators per tile, dC (16 blocks) fills them all
     assert plans["gat_out_head"] == 1 and plans["gat0"] == 0
+    # gat0's X = [fvs | pos_enc] is 16 + 1 blocks: 17 x 17 blocks tile into 125 CTAs with half-empty accumulators, the
+    # two sources on their own into 140 CTAs of full tiles; the evenly tiling concatenations stay one launch
+    assert split_sources["gat0"] == 1 and not any(split_sources[k] for k in ("gat1", "gat2", "gat_out_head"))
     small = (ctypes.c_int32 * 8)()
     assert L.planes_linear_bwd_weight_plan(300, 48, 64, 0, small, 8) == 8 and small[3] == 1 and small[4] == 1
 
