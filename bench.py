@@ -433,6 +433,7 @@ def run_ours(args):
         def e2e_measure(hb, n, what):
             # 3 untimed steps: the first end-to-end steps grow the allocator's pools (two batches are alive at once:
             # cudaMalloc of multi-GB blocks serialises with the GPU) — steady state from the third step on
+            torch.cuda.empty_cache()                     # pools shaped by the end-to-end pattern, not by the legs before
             e2e_run(hb, 3)
             barrier()
             t0 = time.perf_counter()
