@@ -60,6 +60,7 @@ struct TArgs {
     int nmax;                      // rows per z stage (largest graph rounded up to the box)
     int nstages;                   // 1 or 2
     int nslices;                   // H*F / 32
+    int split;                     // CTAs per tree: each takes a contiguous range of the tree's slices (small batches)
 };
 
 struct short4s { short x, y, z, w; };
@@ -71,17 +72,29 @@ __device__ __forceinline__ void issue_slice(const CUtensorMap* map, uint32_t bar
     for (int r = 0; r < nbox; ++r) tma_load_2d(dst + r * (kBoxRows * kCS * 4), map, bar, col, (int)(n0 + r * kBoxRows));
 }
 
-// walks the (tree, slice) items of one CTA
+// walks the (tree, slice) items of one CTA: slices [s0, s1) of trees first, first + tstep, ...  With t.split == 1 a
+// CTA takes whole trees; batches with fewer trees than SMs (the reference trains on 64 scans and infers one scan at a
+// time, job_runner.py:1892-1919, :840-911) give every tree to t.split CTAs, each with its own range of slices.
 struct Cursor {
-    int64_t tr, n0; int n, s;
+    int64_t tr, n0; int n, s; int s0, s1, tstep;
     __device__ __forceinline__ bool valid(const TArgs& t) const { return tr < t.B; }
     __device__ __forceinline__ void load(const TArgs& t) {
         if (tr < t.B) { n0 = t.node_off[tr]; n = (int)(t.node_off[tr + 1] - n0); }
     }
     __device__ __forceinline__ void advance(const TArgs& t) {
-        if (++s == t.nslices) { s = 0; tr += gridDim.x; load(t); }
+        if (++s == s1) { s = s0; tr += tstep; load(t); }
     }
 };
+__device__ __forceinline__ Cursor first_cursor(const TArgs& t) {
+    Cursor c;
+    const int sg = (int)(blockIdx.x % (unsigned)t.split);
+    c.s0 = (int)((int64_t)sg * t.nslices / t.split);
+    c.s1 = (int)((int64_t)(sg + 1) * t.nslices / t.split);
+    c.tstep = (int)(gridDim.x / (unsigned)t.split);
+    c.tr = blockIdx.x / (unsigned)t.split;
+    c.s = c.s0; c.n0 = 0; c.n = 0;
+    return c;
+}
 
 // activation known at compile time (ACT = SPGNN_ACT_ELU / _TANH), else the runtime code
 template <int ACT>
@@ -133,22 +146,22 @@ __global__ void __launch_bounds__(THREADS, 1) gat_tree_fwd_kernel(const __grid_c
     }
     __syncthreads();
 
-    Cursor cur{(int64_t)blockIdx.x, 0, 0, 0};
+    Cursor cur = first_cursor(t);
     if (!cur.valid(t)) return;
     cur.load(t);
     Cursor nxt = cur;            // item whose z slice was issued last
     nxt.advance(t);
     if (threadIdx.x == 0) {
-        issue_slice(&zmap, smem_u32(&st.full[0]), zs_u32, cur.n0, cur.n, 0);
+        issue_slice(&zmap, smem_u32(&st.full[0]), zs_u32, cur.n0, cur.n, cur.s * kCS);
         if (t.nstages == 2 && nxt.valid(t))
             issue_slice(&zmap, smem_u32(&st.full[1]), zs_u32 + stage_bytes, nxt.n0, nxt.n, nxt.s * kCS);
     }
     float4 r[KPER];              // residual rows of the item about to be computed (prefetched one slice ahead)
-    float4 bv = a.bias ? ldg4(a.bias + l8 * 4) : zero4();
+    float4 bv = a.bias ? ldg4(a.bias + cur.s * kCS + l8 * 4) : zero4();
 #pragma unroll
     for (int k = 0; k < KPER; ++k) {
         const int i = qw + k * kQW;
-        r[k] = (has_res && i < cur.n) ? ldg4(a.Y + (cur.n0 + i) * a.ldy + a.res_off + l8 * 4) : zero4();
+        r[k] = (has_res && i < cur.n) ? ldg4(a.Y + (cur.n0 + i) * a.ldy + a.res_off + cur.s * kCS + l8 * 4) : zero4();
     }
 
     for (uint32_t item = 0; cur.valid(t); ++item) {
@@ -156,13 +169,16 @@ __global__ void __launch_bounds__(THREADS, 1) gat_tree_fwd_kernel(const __grid_c
         const uint32_t par = t.nstages == 2 ? ((item >> 1) & 1) : (item & 1);
         const int64_t n0 = cur.n0;
         const int n = cur.n, s = cur.s;
-        if (s == 0) {
-            // ---------------- phase A: edge softmax of the tree, one thread per (node, head)
+        if (s == cur.s0) {
+            // ---------------- phase A: edge softmax of the tree, one thread per (node, head); the attention weights go
+            // to global memory from the CTA that owns the head's first slice
             for (int it = threadIdx.x; it < n * H; it += kThreads) {
                 const int i = it / H, h = it - i * H;
                 const int64_t v = n0 + i;
                 const int beg = __ldg(a.in_ptr + v), deg = __ldg(a.in_ptr + v + 1) - beg;
                 const float er = __ldg(a.Y + v * a.ldy + a.er_off + h);
+                const int hs = h * (F / kCS);
+                const bool own_head = hs >= cur.s0 && hs < cur.s1;
                 int u[4];
                 float e[4], m = -INFINITY;
 #pragma unroll
@@ -178,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) gat_tree_fwd_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float at = p[j] * inv;
-                    if (j < deg) a.att[(int64_t)(beg + j) * H + h] = at;
+                    if (j < deg && own_head) a.att[(int64_t)(beg + j) * H + h] = at;
                     st.w[(i * H + h) * 4 + j] = j < deg ? at * keep_scale(a, beg + j, h) : 0.f;
                 }
                 if (h == 0) {
@@ -339,13 +355,13 @@ __global__ void __launch_bounds__(THREADS, 1) gat_tree_bwd_kernel(const __grid_c
     for (int i = threadIdx.x; i < HF; i += kThreads) st.sb[i] = 0.f;
     __syncthreads();
 
-    Cursor cur{(int64_t)blockIdx.x, 0, 0, 0};
+    Cursor cur = first_cursor(t);
     if (cur.valid(t)) cur.load(t);
     Cursor nxt = cur;
     if (cur.valid(t)) {
         nxt.advance(t);
         if (threadIdx.x == 0) {
-            issue_slice(&zmap, smem_u32(&st.full[0]), zs_u32, cur.n0, cur.n, 0);
+            issue_slice(&zmap, smem_u32(&st.full[0]), zs_u32, cur.n0, cur.n, cur.s * kCS);
             if (t.nstages == 2 && nxt.valid(t))
                 issue_slice(&zmap, smem_u32(&st.full[1]), zs_u32 + stage_bytes, nxt.n0, nxt.n, nxt.s * kCS);
         }
@@ -375,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) gat_tree_bwd_kernel(const __grid_c
         const uint32_t par = t.nstages == 2 ? ((item >> 1) & 1) : (item & 1);
         const int64_t n0 = cur.n0;
         const int n = cur.n, s = cur.s;
-        if (s == 0) {
+        if (s == cur.s0) {
             // ---------------- phase A: stage both edge directions of the tree, one thread per (node, head)
             const int lb0 = __ldg(a.in_ptr + n0);
             for (int it = threadIdx.x; it < n * H; it += kThreads) {
@@ -530,10 +546,13 @@ __global__ void __launch_bounds__(THREADS, 1) gat_tree_bwd_kernel(const __grid_c
             }
         }
         __syncthreads();
-        if (s == t.nslices - 1) {
-            // ---------------- phase C: softmax + LeakyReLU backward of the tree, d(er); then d(el) over out-edges
+        if (s == cur.s1 - 1) {
+            // ---------------- phase C: softmax + LeakyReLU backward of the tree, d(er); then d(el) over out-edges — for
+            // the heads this CTA walked (all of them unless the tree is split by head)
+            const int h_lo = cur.s0 * kCS / F, h_hi = cur.s1 * kCS / F;
             for (int it = threadIdx.x; it < n * H; it += kThreads) {
                 const int i = it / H, hh = it - i * H;
+                if (hh < h_lo || hh >= h_hi) continue;
                 const int deg = st.deg[i], lb = st.beg[i];
                 const int o = (i * H + hh) * 4;
                 float da[4], at[4], wsum = 0.f, der = 0.f;
@@ -557,6 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1) gat_tree_bwd_kernel(const __grid_c
             __syncthreads();
             for (int it = threadIdx.x; it < n * H; it += kThreads) {
                 const int i = it / H, hh = it - i * H;
+                if (hh < h_lo || hh >= h_hi) continue;
                 const int od = st.odeg[i];
                 const short4s sl = st.oslot[i];
                 float del = 0.f;
@@ -639,7 +659,9 @@ static int launch_fwd_cfg(const CUtensorMap& zmap, TArgs& t, const Args& a, cons
         SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         attr.done();
     }
-    const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
+    // fewer trees than SMs: up to nslices CTAs per tree, each with its own slices
+    t.split = L->B < sm_count() ? (int)(sm_count() / L->B < t.nslices ? sm_count() / L->B : t.nslices) : 1;
+    const unsigned grid = (unsigned)(L->B < sm_count() ? L->B * t.split : sm_count());
     fn<<<grid, THREADS, smem, st>>>(zmap, t);
     SPGNN_LAUNCH_OK();
     *handled = true;
@@ -697,7 +719,10 @@ static int launch_bwd_cfg(const CUtensorMap& zmap, TArgs& t, const Args& a, cons
         SPGNN_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         attr.done();
     }
-    const unsigned grid = (unsigned)(L->B < sm_count() ? L->B : sm_count());
+    // fewer than #SMs / H trees: one CTA per (tree, head) — the per-edge dot products of a head accumulate over its
+    // slices inside one CTA, so a head is the finest split the backward takes
+    t.split = (a.H > 1 && L->B * a.H <= sm_count()) ? a.H : 1;
+    const unsigned grid = (unsigned)(L->B < sm_count() ? L->B * t.split : sm_count());
     fn<<<grid, THREADS, smem, st>>>(zmap, t);
     SPGNN_LAUNCH_OK();
     if (L->dbias) {
