@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kPeThreads) pe_dist_tree_kernel(const int64_t*
         __syncthreads();
     }
     // node 0 must have reached every node (a forest plus a cycle has the edge count of a tree)
+    __syncthreads();                                          // every thread has read s_flag and left the loop
     if (tid == 0) s_flag = 0;
     __syncthreads();
     int unreached = 0;
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(kPeThreads) pe_dist_tree_kernel(const int64_t*
     }
     // ---- BFS 2 from the node farthest from node 0: its eccentricity is the diameter of the tree
     const int far = s_far;
-    for (int v = tid; v < n; v += nt) d2[v] = v == far ? 0 : -1;
+    int* mark = reinterpret_cast<int*>(nxt);                  // BFS 1 is over: its spare wave buffer holds the join marks
+    for (int v = tid; v < n; v += nt) { d2[v] = v == far ? 0 : -1; mark[v] = 0; }
     __syncthreads();
     int ecc = 0;
     while (true) {
@@ -207,13 +209,13 @@ __global__ void __launch_bounds__(kPeThreads) pe_dist_tree_kernel(const int64_t*
             if (d2[v] != -1) continue;
             bool hit = false;
             for (int e = ptr[base + v]; e < ptr[base + v + 1]; ++e) hit |= d2[nbr[e] - (int)base] == ecc;
-            if (hit) { d2[v] = -2 - ecc; s_flag = 1; }        // joins level ecc + 1 after the barrier
+            if (hit) { mark[v] = 1; s_flag = 1; }             // joins level ecc + 1 after the barrier (d2 is only read here)
         }
         __syncthreads();
         if (!s_flag) break;                                   // uniform
         ++ecc;
         for (int v = tid; v < n; v += nt)
-            if (d2[v] == -1 - ecc) d2[v] = ecc;
+            if (mark[v]) { d2[v] = ecc; mark[v] = 0; }
         __syncthreads();
     }
     if (tid == 0) { diam[blockIdx.x] = ecc; done[blockIdx.x] = 1; }
