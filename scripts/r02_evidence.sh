@@ -16,6 +16,7 @@ ls -la /tmp/full_step.ncu-rep
 python scripts/ncu_traffic.py /tmp/full_step.ncu-rep ${P}_ncu_traffic.json 4096 > ${P}_ncu_table.txt 2>&1; cat ${P}_ncu_table.txt
 python scripts/ncu_summary.py /tmp/full_step.ncu-rep 10 > ${P}_ncu_full_summary.txt 2>&1
 ncu -i /tmp/full_step.ncu-rep --page raw --csv 2>/dev/null | gzip > ${P}_ncu_raw.csv.gz
+if [ -n "$SKIP_CONFIGS" ]; then ls -la gpurun_out | tail -20; exit 0; fi      # other-config lines unchanged since the last pass
 : > ${P}_configs.jsonl
 for w in st_gat_3 st_gat_6 st_gat_6_nr st_gcn_3 st_gin_3 st_sage_3; do
   timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-e2e --no-cpu --no-small --stream-steps 0 >> ${P}_configs.jsonl 2>> ${P}_bench.err
