@@ -244,6 +244,27 @@ def from_edges(src, dst, num_nodes, device=None):
                                  torch.tensor([s.numel()], dtype=torch.int64, device=dev), s, d, max_nodes=num_nodes)
 
 
+def DGLGraph(data=None, device=None):
+    """``dgl.DGLGraph(nx_graph)`` as the reference calls it (job_runner.py:1781-1783: ``DGLGraph(nx.DiGraph(adj))``):
+    nodes 0..n-1 in sorted order, edges in ``nx_graph.edges()`` order (DGL's from_networkx for a graph without edge
+    ids); an undirected graph contributes both directions.  A dense adjacency (numpy / tensor) is accepted as well and
+    means ``DGLGraph(nx.DiGraph(adj))`` — non-zero entries row-major, self loops where the diagonal has them."""
+    if data is None:
+        raise SpgnnError("DGLGraph(): an empty graph cannot be grown node by node here; pass a networkx graph or an adjacency")
+    if hasattr(data, "edges") and hasattr(data, "number_of_nodes"):          # networkx Graph / DiGraph
+        if not data.is_directed():
+            data = data.to_directed()
+        nodes = sorted(data.nodes())
+        index = {v: i for i, v in enumerate(nodes)}
+        e = np.asarray([(index[u], index[v]) for u, v in data.edges()], dtype=np.int64).reshape(-1, 2)
+        return from_edges(e[:, 0], e[:, 1], len(nodes), device)
+    adj = data.detach().cpu().numpy() if isinstance(data, torch.Tensor) else np.asarray(data)
+    if adj.ndim != 2 or adj.shape[0] != adj.shape[1]:
+        raise SpgnnError("adjacency must be square")
+    src, dst = np.nonzero(adj)                                                # row-major: nx.DiGraph(adj).edges() order
+    return from_edges(src.astype(np.int64), dst.astype(np.int64), adj.shape[0], device)
+
+
 def to_networkx(g):
     return g.to_networkx()
 

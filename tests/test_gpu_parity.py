@@ -73,6 +73,29 @@ def test_batch_builder_matches_reference_fixture(mods):
     assert torch.equal(g2.src, g.src) and torch.equal(g2.dst, g.dst) and torch.equal(g2.in_src, g.in_src)
 
 
+def test_from_adj_to_graph_ports_line_by_line(mods):
+    """job_runner.py:1779-1801 with ``spgnn_b200.graph`` standing in for ``dgl``: DGLGraph(nx.DiGraph(adj)) →
+    remove_self_loop → .to('cuda:0') → ndata → add_edges(nodes, nodes) gives the edge lists the reference's own code
+    produced (fixture), and equals the one-pass builder."""
+    import networkx as nx
+    sg = mods["sg"]
+    rec, scans = golden_graph_inputs()
+    for i, s in enumerate(scans):
+        adj_np = np.asarray(s["adj"])
+        for first in (nx.DiGraph(adj_np), adj_np, torch.from_numpy(adj_np)):
+            g = sg.DGLGraph(first)
+            g = sg.remove_self_loop(g)
+            g = g.to('cuda:0')
+            g.ndata['y'] = torch.from_numpy(np.asarray(s["labels"]).astype(np.int64)).cuda()
+            g.add_edges(g.nodes(), g.nodes())
+            assert np.array_equal(g.src.cpu().numpy(), rec[f"src{i}"]) and np.array_equal(g.dst.cpu().numpy(), rec[f"dst{i}"])
+            assert g.number_of_nodes() == adj_np.shape[0] and g.ndata['y'].shape[0] == adj_np.shape[0]
+        h = sg.from_adj(adj_np)
+        assert torch.equal(h.in_src, g.in_src) and torch.equal(h.in_ptr, g.in_ptr) and torch.equal(h.out_dst, g.out_dst)
+    und = nx.path_graph(4)                                   # an undirected graph contributes both directions
+    assert sg.DGLGraph(und).number_of_edges() == 6
+
+
 def test_batch_builder_csc_csr_consistency_ragged_64(mods):
     scans = _scan_dicts(mods, 0, 64, ragged=True, fv_dim=4)
     g = mods["sg"].batch_from_adjs([s["adj"] for s in scans])
