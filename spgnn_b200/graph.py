@@ -111,7 +111,11 @@ class Graph:
         return self
 
     def cpu(self):
-        raise SpgnnError("spgnn_b200 graphs live on CUDA devices only (use .edges() / .ndata[...] .cpu() for host copies)")
+        """``g.cpu()``: a read-only host copy (:class:`HostGraph`) for the host-side helpers the reference runs on it —
+        ``dgl.to_networkx(g.cpu())`` (job_runner.py:1763), ``g.cpu().to_networkx()`` (:1652),
+        ``adjacency_matrix().to_dense().numpy()`` (:1742).  The kernels never take it: ``.to('cuda')`` gives back the
+        device graph it was copied from."""
+        return HostGraph(self)
 
     def local_var(self):
         return self
@@ -187,6 +191,75 @@ class Graph:
         if self.zero_in_degree:
             raise SpgnnError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid "
                              "(DGLError in the reference stack); add self loops or pass allow_zero_in_degree=True")
+
+
+class HostGraph:
+    """Host copy of a device graph's structure (edge lists in edge-id order) and node data: what ``Graph.cpu()`` returns.
+    Read-only DGLGraph subset — sizes, ``nodes`` / ``edges``, degrees, adjacency (dense tensor, scipy), networkx."""
+
+    def __init__(self, g):
+        self._device_graph = g
+        self.src, self.dst = g.src.cpu(), g.dst.cpu()
+        self.num_nodes, self.num_edges = int(g.num_nodes), int(self.src.numel())
+        self.batch_size = g.batch_size
+        self._bnn, self._bne = g._bnn.cpu(), g._bne.cpu()
+        self.ndata = {k: v.cpu() for k, v in g.ndata.items()}
+        self.device = torch.device("cpu")
+
+    def number_of_nodes(self):
+        return self.num_nodes
+
+    def number_of_edges(self):
+        return self.num_edges
+
+    def nodes(self):
+        return torch.arange(self.num_nodes, dtype=torch.int64)
+
+    def edges(self):
+        return self.src, self.dst
+
+    def batch_num_nodes(self):
+        return self._bnn
+
+    def batch_num_edges(self):
+        return self._bne
+
+    def in_degrees(self):
+        return torch.bincount(self.dst, minlength=self.num_nodes)
+
+    def out_degrees(self):
+        return torch.bincount(self.src, minlength=self.num_nodes)
+
+    def to(self, device=None, **_):
+        if device is None or torch.device(device).type == "cpu":
+            return self
+        return self._device_graph.to(device)
+
+    def cpu(self):
+        return self
+
+    def adjacency_matrix(self, transpose=False, scipy_fmt=None):
+        if scipy_fmt is not None:
+            return self.adjacency_matrix_scipy(transpose=transpose, fmt=scipy_fmt)
+        a = torch.zeros(self.num_nodes, self.num_nodes)
+        a[self.src, self.dst] = 1.0
+        return a.t() if transpose else a
+
+    def adjacency_matrix_scipy(self, transpose=False, fmt="csr", return_edge_ids=False):
+        import scipy.sparse as sp
+        s, d = self.src.numpy(), self.dst.numpy()
+        if transpose:
+            s, d = d, s
+        vals = np.arange(self.num_edges) if return_edge_ids else np.ones(self.num_edges)
+        return sp.coo_matrix((vals, (s, d)), shape=(self.num_nodes, self.num_nodes)).asformat(fmt)
+
+    def to_networkx(self):
+        import networkx as nx
+        G = nx.MultiDiGraph()
+        G.add_nodes_from(range(self.num_nodes))
+        for i, (u, v) in enumerate(zip(self.src.tolist(), self.dst.tolist())):
+            G.add_edge(u, v, id=i)
+        return G
 
 
 # -------------------------------------------------------------------- builders

@@ -94,6 +94,19 @@ def test_from_adj_to_graph_ports_line_by_line(mods):
         assert torch.equal(h.in_src, g.in_src) and torch.equal(h.in_ptr, g.in_ptr) and torch.equal(h.out_dst, g.out_dst)
     und = nx.path_graph(4)                                   # an undirected graph contributes both directions
     assert sg.DGLGraph(und).number_of_edges() == 6
+    # the host-side helpers of the reference run on g.cpu(): dgl.to_networkx(g.cpu()) (job_runner.py:1763),
+    # g.cpu().to_networkx() (:1652), adjacency_matrix().to_dense().numpy() (:1742), in_degrees() (:1633)
+    hg = g.cpu()
+    G1, G2 = sg.to_networkx(hg), hg.to_networkx()
+    by_id = lambda G: [(u, v) for u, v, _ in sorted(G.edges(data="id"), key=lambda e: e[2])]
+    assert by_id(G1) == by_id(G2) == list(zip(rec[f"src{i}"].tolist(), rec[f"dst{i}"].tolist()))
+    assert list(G1.edges()) == list(g.to_networkx().edges())
+    assert nx.diameter(G1) >= 1 and hg.number_of_nodes() == g.number_of_nodes()
+    A = hg.adjacency_matrix().to_dense().numpy()
+    assert np.array_equal(A, g.adjacency_matrix().cpu().numpy()) and A.sum() == g.number_of_edges()
+    assert np.array_equal(hg.in_degrees().numpy(), g.in_degrees().cpu().numpy())
+    assert (hg.adjacency_matrix(scipy_fmt="csr") != g.adjacency_matrix(scipy_fmt="csr")).nnz == 0
+    assert torch.equal(hg.ndata['y'], g.ndata['y'].cpu()) and hg.to('cuda:0') is g and hg.cpu() is hg
 
 
 def test_batch_builder_csc_csr_consistency_ragged_64(mods):
