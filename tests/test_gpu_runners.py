@@ -170,6 +170,59 @@ def test_packed_wire_format_decodes_to_the_dense_batch_bit_for_bit():
     assert torch.equal(a.ndata["pos_enc"], b.ndata["pos_enc"]) and torch.equal(a.ndata["fvs"], b.ndata["fvs"])
 
 
+def test_the_reference_training_loop_runs_verbatim_on_the_models():
+    """The body of GCNTrainSPGNN.train's GCN_STEPS loop (job_runner.py:1885-1919) written as the reference writes it —
+    numpy sampling table, Python list-comprehension mask, ``F.cross_entropy(gnn_out[mask], labels[mask], weight=)``,
+    ``torch.optim.SGD`` — on a spgnn_b200 model, against runner.train_step (fused masked CE + FlatSGD) fed the same
+    masks: same losses step by step and the same parameters afterwards."""
+    import torch.nn.functional as F
+    import test_gpu_parity as T
+    from spgnn_b200 import graph as sg, models as sm, ops, pe as spe, runner, synth
+    from spgnn_b200.settings import PRESETS
+    cfg = dict(PRESETS["st_pgat_spgnn_3"]["MODEL"])
+    cfg.pop("method")
+    cfg.update(feat_drop=0.0, attn_drop=0.0)
+    m = dict(sg=sg, synth=synth)
+    scans = T._scan_dicts(m, 40, 5)
+    batch_g = T._device_batch(m, scans)
+    batch_g.ndata["y"] = torch.from_numpy(np.concatenate([s["labels"] for s in scans]).astype(np.int64)).cuda()
+    spe.distance_pos_enc(batch_g, pos_enc_dim=39)
+    torch.manual_seed(0)
+    model = sm.GATPositionSPGNNNet(**cfg).cuda()
+    model.init(); model.train(); model.set_gcn_only()
+    twin = sm.GATPositionSPGNNNet(**cfg).cuda()
+    twin.load_state_dict(model.state_dict()); twin.train(); twin.set_gcn_only()
+    GCN_STEPS, sampling_rate = 4, 0.3
+    weight_t = torch.tensor(runner.CLASS_WEIGHTS_22, device="cuda")
+    optimizer = torch.optim.SGD(model.parameters(), lr=5e-3, momentum=0.9)
+    flat = runner.FlatSGD(twin.parameters(), lr=5e-3, momentum=0.9)
+    # ---- reference lines
+    n_nodes = [batch_g.number_of_nodes()]
+    labels_list_cat = batch_g.ndata['y']
+    sampling_t = torch.ones_like(labels_list_cat, dtype=torch.float32) * sampling_rate
+    sampling_t[labels_list_cat.nonzero(as_tuple=True)] = 1.0
+    sampling_t = sampling_t.detach().cpu().numpy()
+    np.random.seed(3)
+    random_list = np.random.random_sample(GCN_STEPS * sum(n_nodes)).reshape(GCN_STEPS, sum(n_nodes))
+    ref_losses, our_losses = [], []
+    for n in range(GCN_STEPS):
+        optimizer.zero_grad()
+        mask = [rn < sampling_t[k] for k, rn in zip(range(sum(n_nodes)), random_list[n])]
+        assert (all([mask[x.item()] for x in labels_list_cat.nonzero()]))
+        gnn_out, n_embed, p_embed = model(batch_g)
+        loss_gnn = F.cross_entropy(gnn_out[mask], labels_list_cat[mask], weight=weight_t)
+        loss_gnn.backward()
+        ref_losses.append(loss_gnn.item())
+        optimizer.step()
+        # ---- the runner's step on the twin, same mask
+        mt = torch.from_numpy(np.asarray(mask)).cuda()
+        our_losses.append(float(runner.train_step(twin, batch_g, flat, weight_t, sampling_rate, mask=mt).item()))
+    assert np.isfinite(ref_losses).all() and ref_losses[-1] < ref_losses[0]
+    assert np.allclose(ref_losses, our_losses, rtol=2e-5, atol=1e-6), (ref_losses, our_losses)
+    for (k, a), b in zip(model.state_dict().items(), twin.state_dict().values()):
+        assert T.rel_err(b, a) < 1e-4, k
+
+
 def test_seed_salt_changes_every_mask_and_resets():
     """spgnn_seed_salt_set: the same (p, seed) draws a different dropout mask under a different salt (what lets a
     CUDA-graph replay of a step draw fresh masks although its seeds are frozen kernel arguments), salt 0 restores it."""
